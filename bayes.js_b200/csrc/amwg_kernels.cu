@@ -1,0 +1,919 @@
+// amwg_kernels.cu -- libamwg_b200.so: the AMWG hot path of bayes.js as sm_100a CUDA + the C ABI of include/amwg.h.
+//
+// Reference path replaced (all under /root/reference/):
+//   Sampler.sample / burn / step                     mcmc.js:985-1039
+//   AmwgStepper.step (in-place substepper shuffle)    mcmc.js:886-892
+//   MultidimComponentMetropolisStepper.step           mcmc.js:685-688  (nested_array_random_apply :244-263)
+//   OnedimMetropolisStepper.step (+ batch adaptation) mcmc.js:517-553
+//   BinaryStepper.step                                mcmc.js:753-767
+//   rnorm / shuffle_array                             mcmc.js:43-54, 228-236
+//   user log_post -> ld.*                             distributions.js (per opcode, amwg_ld.cuh)
+//
+// One thread per chain.  Per-chain state is SoA in HBM ([component][chain], coalesced); data[] is staged into
+// shared memory once per CTA by 1-D bulk TMA (cp.async.bulk + mbarrier) and read as warp broadcasts.
+// The current log-density is cached per chain: log_post is a pure function of the state, so the reference's
+// first evaluation of every step (mcmc.js:524) returns exactly the value cached here (DESIGN.md "one eval per step").
+// Compiled with --fmad=false; fma() is written out only inside the factorised plates.
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "../../include/amwg.h"
+#include "amwg_math.cuh"
+#include "amwg_ld.cuh"
+
+namespace amwg {
+
+constexpr int kMaxColumns = 16;
+constexpr int kMaxParams = 16;       // substepper order is packed 4 bits per named parameter
+constexpr int kMaxDim0 = 256;        // top-level visit order of a multi-dim parameter (uint8 per entry)
+constexpr int kMaxDerived = 8;
+constexpr int kStack = 16;
+constexpr int kThreads = 128;
+constexpr int kAdaptChunk = 64;
+constexpr unsigned kSmemBudget = 200u * 1024u;   // bytes of dynamic shared memory we are willing to fill with data
+
+// ---- model image as the kernels see it (passed by value) ------------------------------------------------------
+struct ModelDev {
+  const unsigned char* image;      // global: [code | consts | plates | params] packed, 16B aligned sections
+  unsigned image_bytes;            // multiple of 16
+  unsigned off_code, off_consts, off_plates, off_params;
+  const double* col_global[kMaxColumns];
+  unsigned col_bytes[kMaxColumns];     // padded to 16
+  int col_smem_off[kMaxColumns];       // byte offset in dynamic smem, or -1: read from global/L2
+  int n_columns, n_plates, n_params, D, n_derived;
+  int logpost_prog, derived_prog;
+  const unsigned char* adapting;   // [D] global, host-maintained (start/stop_adaptation)
+};
+
+struct ChainArrays {
+  double* state;          // [D][C]
+  double* pls;            // [D][C] prop_log_scale
+  int* acc;               // [D][C] acceptance_count of the current batch
+  double* curr_lp;        // [C]   cached log_post(state)
+  unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
+  unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
+  unsigned long long C;
+  unsigned long long first_chain;
+  unsigned long long seed;
+};
+
+struct SweepArgs {
+  long long n_sweeps;
+  long long sample_i0;     // index i of the first sweep within the current sample() call
+  long long thin;
+  int record;              // 0: burn, 1: sample
+  int n_monitor;
+  const int* monitor;      // global [n_monitor]
+  double* out;             // [row][monitor][chain]
+};
+
+struct Ctx {                       // lives in shared memory
+  const int* code;
+  const double* consts;
+  const amwg_plate* plates;
+  const amwg_param* params;
+  const double* col[kMaxColumns];
+};
+
+struct EvalState {
+  const double* st;   // state base + chain
+  unsigned long long stride;
+  int moved;          // component carrying the proposal, or -1
+  double val;
+  __device__ __forceinline__ double comp(int c) const { return c == moved ? val : st[(unsigned long long)c * stride]; }
+};
+
+// ---- TMA 1-D bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
+          smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// Stage the model image and every data column that fits into shared memory; fill ctx. All threads call this.
+__device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* smem, Ctx& ctx, unsigned long long* bar) {
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned total = m.image_bytes;
+    for (int k = 0; k < m.n_columns; ++k)
+      if (m.col_smem_off[k] >= 0) total += m.col_bytes[k];
+    mbar_expect_tx(bar, total);
+    tma_bulk_g2s(smem, m.image, m.image_bytes, bar);
+    for (int k = 0; k < m.n_columns; ++k)
+      if (m.col_smem_off[k] >= 0) tma_bulk_g2s(smem + m.col_smem_off[k], m.col_global[k], m.col_bytes[k], bar);
+    ctx.code = reinterpret_cast<const int*>(smem + m.off_code);
+    ctx.consts = reinterpret_cast<const double*>(smem + m.off_consts);
+    ctx.plates = reinterpret_cast<const amwg_plate*>(smem + m.off_plates);
+    ctx.params = reinterpret_cast<const amwg_param*>(smem + m.off_params);
+    for (int k = 0; k < m.n_columns; ++k)
+      ctx.col[k] = m.col_smem_off[k] >= 0 ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
+  }
+  __syncthreads();
+  mbar_wait(bar, 0);
+}
+
+// ---- expression interpreter -----------------------------------------------------------------------------------
+// Executes one non-accumulating instruction on the stack. Returns false for END/ACC/PLATE/STORE (caller handles).
+__device__ __forceinline__ bool exec_basic(const Ctx& ctx, const EvalState& es, int op, int a, int& pc, double* stk, int& sp, int plate_i) {
+  switch (op) {
+    case AMWG_OP_CONST: stk[sp++] = ctx.consts[a]; return true;
+    case AMWG_OP_COMP: stk[sp++] = es.comp(a); return true;
+    case AMWG_OP_DATA: stk[sp++] = ctx.col[a][ctx.code[pc++]]; return true;
+    case AMWG_OP_DATA_I: { int off = ctx.code[pc++], stride = ctx.code[pc++]; stk[sp++] = ctx.col[a][off + stride * plate_i]; return true; }
+    case AMWG_OP_COMP_I: {
+      int off = ctx.code[pc++], stride = ctx.code[pc++], base = ctx.code[pc++];
+      stk[sp++] = es.comp(base + (int)ctx.col[a][off + stride * plate_i]);
+      return true;
+    }
+    case AMWG_OP_ADD: sp--; stk[sp - 1] = stk[sp - 1] + stk[sp]; return true;
+    case AMWG_OP_SUB: sp--; stk[sp - 1] = stk[sp - 1] - stk[sp]; return true;
+    case AMWG_OP_MUL: sp--; stk[sp - 1] = stk[sp - 1] * stk[sp]; return true;
+    case AMWG_OP_DIV: sp--; stk[sp - 1] = stk[sp - 1] / stk[sp]; return true;
+    case AMWG_OP_NEG: stk[sp - 1] = -stk[sp - 1]; return true;
+    case AMWG_OP_LOG: stk[sp - 1] = js_log(stk[sp - 1]); return true;
+    case AMWG_OP_EXP: stk[sp - 1] = js_exp(stk[sp - 1]); return true;
+    case AMWG_OP_SQRT: stk[sp - 1] = sqrt(stk[sp - 1]); return true;
+    case AMWG_OP_ABS: stk[sp - 1] = fabs(stk[sp - 1]); return true;
+    case AMWG_OP_POW: sp--; stk[sp - 1] = js_pow(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LT: sp--; stk[sp - 1] = stk[sp - 1] < stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_LE: sp--; stk[sp - 1] = stk[sp - 1] <= stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_GT: sp--; stk[sp - 1] = stk[sp - 1] > stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_GE: sp--; stk[sp - 1] = stk[sp - 1] >= stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_EQ: sp--; stk[sp - 1] = stk[sp - 1] == stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_NE: sp--; stk[sp - 1] = stk[sp - 1] != stk[sp] ? 1.0 : 0.0; return true;
+    case AMWG_OP_AND: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 && stk[sp] != 0.0) ? 1.0 : 0.0; return true;
+    case AMWG_OP_OR: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 || stk[sp] != 0.0) ? 1.0 : 0.0; return true;
+    case AMWG_OP_NOT: stk[sp - 1] = stk[sp - 1] != 0.0 ? 0.0 : 1.0; return true;
+    case AMWG_OP_SELECT: sp -= 2; stk[sp - 1] = stk[sp - 1] != 0.0 ? stk[sp] : stk[sp + 1]; return true;
+    case AMWG_OP_LGAMMA: stk[sp - 1] = ld_lgamma(stk[sp - 1]); return true;
+    case AMWG_OP_LFACTORIAL: stk[sp - 1] = ld_lfactorial(stk[sp - 1]); return true;
+    case AMWG_OP_LCHOOSE: sp--; stk[sp - 1] = ld_lchoose(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LBETA: sp--; stk[sp - 1] = ld_lbeta(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LD_NORM: sp -= 2; stk[sp - 1] = ld_norm(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_UNIF: sp -= 2; stk[sp - 1] = ld_unif(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_BETA: sp -= 2; stk[sp - 1] = ld_beta(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_BERN: sp--; stk[sp - 1] = ld_bern(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LD_POIS: sp--; stk[sp - 1] = ld_pois(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LD_CAUCHY: sp -= 2; stk[sp - 1] = ld_cauchy(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_LAPLACE: sp -= 2; stk[sp - 1] = ld_laplace(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_GAMMA: sp -= 2; stk[sp - 1] = ld_gamma(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_INVGAMMA: sp -= 2; stk[sp - 1] = ld_invgamma(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_LNORM: sp -= 2; stk[sp - 1] = ld_lnorm(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_PARETO: sp -= 2; stk[sp - 1] = ld_pareto(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_T: sp -= 3; stk[sp - 1] = ld_t(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); return true;
+    case AMWG_OP_LD_WEIBULL: sp -= 2; stk[sp - 1] = ld_weibull(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_LOGIS: sp -= 2; stk[sp - 1] = ld_logis(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_EXP: sp--; stk[sp - 1] = ld_exp(stk[sp - 1], stk[sp]); return true;
+    case AMWG_OP_LD_BINOM: sp -= 2; stk[sp - 1] = ld_binom(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_NBINOM: sp -= 2; stk[sp - 1] = ld_nbinom(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
+    case AMWG_OP_LD_HYPER: sp -= 3; stk[sp - 1] = ld_hyper(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); return true;
+    default: return false;
+  }
+}
+
+// Evaluate an END-terminated expression program; returns the top of stack.
+__device__ __noinline__ double eval_expr(const Ctx& ctx, const EvalState& es, int pc, int plate_i) {
+  double stk[kStack];
+  int sp = 0;
+  for (;;) {
+    int w = ctx.code[pc++];
+    int op = w & 0xff, a = w >> 8;
+    if (!exec_basic(ctx, es, op, a, pc, stk, sp, plate_i)) break;
+  }
+  return sp > 0 ? stk[sp - 1] : 0.0;
+}
+
+// ---- plates: the O(N) likelihood sums -----------------------------------------------------------------------------
+// sum_i ld.norm(x_i, mean, sd), factorised (amwg.h AMWG_PLATE_NORM_IID). 2 fp64 pipe instructions per point
+// (DADD + DFMA), x_i read as 16-byte warp-broadcast shared-memory loads, 4 independent accumulators.
+__device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, int n, double mean) {
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int i = 0;
+  if ((reinterpret_cast<unsigned long long>(x) & 15ull) && n > 0) { double d = x[0] - mean; s3 = fma(d, d, s3); i = 1; }   // 16B-align the vector loads
+#pragma unroll 4
+  for (; i + 4 <= n; i += 4) {
+    double2 a = *reinterpret_cast<const double2*>(x + i);
+    double2 b = *reinterpret_cast<const double2*>(x + i + 2);
+    double d0 = a.x - mean, d1 = a.y - mean, d2 = b.x - mean, d3 = b.y - mean;
+    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+  }
+  for (; i < n; ++i) { double d = x[i] - mean; s0 = fma(d, d, s0); }
+  return (s0 + s1) + (s2 + s3);
+}
+
+__device__ __forceinline__ double plate_norm_iid(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+  double mean = eval_expr(ctx, es, pl.arg_prog[0], 0);
+  double sd = eval_expr(ctx, es, pl.arg_prog[1], 0);
+  double S = sum_sq_dev(ctx.col[pl.col[0]] + pl.iparam[2], pl.n, mean);
+  double c0 = -0.5 * js_log(2 * AMWG_JS_PI);
+  return lp + ((double)pl.n * (c0 - js_log(sd)) - S / (2 * sd * sd));
+}
+
+// sum_i ld.bern(y_i, p): sequential, bit-faithful to distributions.js:228-230 (x*prob + (1-x)*(1-prob) is exact for x in {0,1}).
+__device__ __forceinline__ double plate_bern_iid(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+  double p = eval_expr(ctx, es, pl.arg_prog[0], 0);
+  double l1 = js_log(1.0 * p + (1 - 1.0) * (1 - p));
+  double l0 = js_log(0.0 * p + (1 - 0.0) * (1 - p));
+  const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
+  for (int i = 0; i < pl.n; ++i) {
+    double yi = y[i];
+    lp = lp + (yi == 1.0 ? l1 : (yi == 0.0 ? l0 : -CUDART_INF));
+  }
+  return lp;
+}
+
+// sum_i ld.norm(y_i, mu[g_i], sd) with points sorted by group; group j occupies [start[j], start[j+1]).
+__device__ __forceinline__ double plate_norm_grouped(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+  double sd = eval_expr(ctx, es, pl.arg_prog[1], 0);
+  const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
+  const double* __restrict__ start = ctx.col[pl.col[1]];
+  int J = pl.iparam[1], base = pl.iparam[0];
+  double S = 0.0;
+  for (int j = 0; j < J; ++j) {
+    int a = (int)start[j], b = (int)start[j + 1];
+    S = S + sum_sq_dev(y + a, b - a, es.comp(base + j));
+  }
+  double c0 = -0.5 * js_log(2 * AMWG_JS_PI);
+  return lp + ((double)pl.n * (c0 - js_log(sd)) - S / (2 * sd * sd));
+}
+
+// sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop), using log(exp(eta)) -> eta
+// and the precomputed lfactorial(y_i) column:  y*eta - exp(eta) - lfact.  (KS-level parity; real parameters only.)
+__device__ __forceinline__ double plate_pois_loglin(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+  const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
+  const double* __restrict__ X = ctx.col[pl.col[1]];
+  const double* __restrict__ lf = ctx.col[pl.col[2]];
+  int K = pl.iparam[1], base = pl.iparam[0];
+  double beta[16];
+  for (int k = 0; k < K && k < 16; ++k) beta[k] = es.comp(base + k);
+  double s0 = 0.0, s1 = 0.0;
+  for (int i = 0; i < pl.n; ++i) {
+    double eta = 0.0;
+    for (int k = 0; k < K; ++k) eta = fma(X[(long long)i * K + k], beta[k], eta);
+    double t = fma(y[i], eta, -exp(eta)) - lf[i];
+    if (i & 1) s1 += t; else s0 += t;
+  }
+  return lp + (s0 + s1);
+}
+
+__device__ __forceinline__ double plate_generic(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+  for (int i = 0; i < pl.n; ++i) lp = lp + eval_expr(ctx, es, pl.body_prog, i);
+  return lp;
+}
+
+// log_post(state with component `moved` replaced by `val`): terms accumulate in program order.
+__device__ __noinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
+  double stk[kStack];
+  int sp = 0;
+  double lp = 0.0;
+  for (;;) {
+    int w = ctx.code[pc++];
+    int op = w & 0xff, a = w >> 8;
+    if (exec_basic(ctx, es, op, a, pc, stk, sp, 0)) continue;
+    if (op == AMWG_OP_ACC) { lp = lp + stk[--sp]; continue; }
+    if (op == AMWG_OP_PLATE) {
+      const amwg_plate& pl = ctx.plates[a];
+      switch (pl.kind) {
+        case AMWG_PLATE_NORM_IID: lp = plate_norm_iid(ctx, pl, es, lp); break;
+        case AMWG_PLATE_BERN_IID: lp = plate_bern_iid(ctx, pl, es, lp); break;
+        case AMWG_PLATE_NORM_GROUPED: lp = plate_norm_grouped(ctx, pl, es, lp); break;
+        case AMWG_PLATE_POIS_LOGLIN: lp = plate_pois_loglin(ctx, pl, es, lp); break;
+        default: lp = plate_generic(ctx, pl, es, lp); break;
+      }
+      continue;
+    }
+    break;  // END
+  }
+  return lp;
+}
+
+// derived quantities (state keys the model adds, mcmc.js:961-963, 990-995): program of <expr> STORE d
+__device__ __noinline__ void eval_derived(const Ctx& ctx, const EvalState& es, int pc, double* der) {
+  double stk[kStack];
+  int sp = 0;
+  for (;;) {
+    int w = ctx.code[pc++];
+    int op = w & 0xff, a = w >> 8;
+    if (exec_basic(ctx, es, op, a, pc, stk, sp, 0)) continue;
+    if (op == AMWG_OP_STORE) { der[a] = stk[--sp]; continue; }
+    break;
+  }
+}
+
+// ---- K0: place every chain at init and evaluate log_post once (Sampler ctor, mcmc.js:954-963) -------------------------
+__global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainArrays a, const double* __restrict__ init,
+                                                            const double* __restrict__ pls0) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+  unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= a.C) return;
+  for (int c = 0; c < m.D; ++c) {
+    a.state[(unsigned long long)c * a.C + chain] = init[c];
+    a.pls[(unsigned long long)c * a.C + chain] = pls0[c];
+    a.acc[(unsigned long long)c * a.C + chain] = 0;
+  }
+  unsigned long long perm = 0;
+  for (int p = 0; p < m.n_params; ++p) perm |= (unsigned long long)p << (4 * p);
+  a.perm[chain] = perm;
+  a.rng_n[chain] = 0;
+  EvalState es{a.state + chain, a.C, -1, 0.0};
+  a.curr_lp[chain] = eval_logpost(ctx, es, m.logpost_prog);
+}
+
+// ---- K1: n_sweeps Sampler.step()s per chain, samples recorded before each kept sweep --------------------------------
+__global__ void __launch_bounds__(kThreads) amwg_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+
+  const unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= a.C) return;
+  const unsigned long long C = a.C;
+  double* st = a.state + chain;
+  double* pls = a.pls + chain;
+  int* acc = a.acc + chain;
+
+  RandomStream g;
+  g.init(a.seed, a.first_chain + chain, a.rng_n[chain]);
+  unsigned long long perm = a.perm[chain];
+  double curr = a.curr_lp[chain];
+  const int P = m.n_params;
+  unsigned char order[kMaxDim0];
+
+  for (long long s = 0; s < sa.n_sweeps; ++s) {
+    // -- Sampler.sample: record the state BEFORE stepping (mcmc.js:1021-1027)
+    if (sa.record) {
+      long long i = sa.sample_i0 + s;
+      if (i % sa.thin == 0) {
+        long long row = i / sa.thin;
+        double der[kMaxDerived];
+        bool have_der = false;
+        for (int j = 0; j < sa.n_monitor; ++j) {
+          int e = sa.monitor[j];
+          double v;
+          if (e < m.D) {
+            v = st[(unsigned long long)e * C];
+          } else {
+            if (!have_der) { EvalState es{st, C, -1, 0.0}; eval_derived(ctx, es, m.derived_prog, der); have_der = true; }
+            v = der[e - m.D];
+          }
+          sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
+        }
+      }
+    }
+    // -- AmwgStepper.step: shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
+    for (int i = P - 1; i > 0; --i) {
+      int j = (int)floor(g.next() * (i + 1));
+      unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
+      perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
+      perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+    }
+    for (int slot = 0; slot < P; ++slot) {
+      const amwg_param pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];
+      const int n_rounds = pa.n_comp;
+      const int inner = pa.n_comp / pa.dim0;
+      if (pa.n_comp > 1) {
+        // nested_array_random_apply: fresh identity, shuffled, top level only (mcmc.js:246-252)
+        for (int i = 0; i < pa.dim0; ++i) order[i] = (unsigned char)i;
+        for (int i = pa.dim0 - 1; i > 0; --i) {
+          int j = (int)floor(g.next() * (i + 1));
+          unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
+        }
+      }
+      for (int r = 0; r < n_rounds; ++r) {
+        int c = pa.comp_offset;
+        if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        const unsigned long long ci = (unsigned long long)c * C;
+        const double cur = st[ci];
+        double prop;
+        bool need;
+        if (pa.type == AMWG_BINARY) {
+          prop = (cur == 0.0) ? 1.0 : 0.0;               // the state value whose log_post is not cached
+          need = true;
+        } else {
+          // generate_proposal (mcmc.js:519, 577-579 / 596-598) and the bounds check (:520)
+          prop = js_rnorm(g, cur, js_exp(pls[ci]));
+          if (pa.type == AMWG_INT) prop = js_round(prop);
+          need = !(prop < pa.lower || prop > pa.upper);
+        }
+        __syncwarp(__activemask());
+        double lp_new = 0.0;
+        if (need) {
+          EvalState es{st, C, c, prop};
+          lp_new = eval_logpost(ctx, es, m.logpost_prog);
+        }
+        if (pa.type == AMWG_BINARY) {
+          // BinaryStepper.step (mcmc.js:753-767); log_post of the current value is the cached one
+          double z0raw = (cur == 0.0) ? curr : lp_new, z1raw = (cur == 0.0) ? lp_new : curr;
+          double mx = js_max(z0raw, z1raw);
+          double z0 = z0raw - mx, z1 = z1raw - mx;
+          double zero_prob = js_exp(z0 - js_log(js_exp(z0) + js_exp(z1)));
+          if (g.next() < zero_prob) { st[ci] = 0.0; curr = z0raw; }
+          else { st[ci] = 1.0; curr = z1raw; }
+        } else if (need) {
+          // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
+          double accept_prob = js_exp(lp_new - curr);
+          if (accept_prob > g.next()) {
+            st[ci] = prop;
+            curr = lp_new;
+            if (m.adapting[c]) acc[ci] += 1;
+          }
+        }
+      }
+    }
+  }
+  a.rng_n[chain] = g.n;
+  a.perm[chain] = perm;
+  a.curr_lp[chain] = curr;
+}
+
+// ---- K2: Roberts-Rosenthal batch update of prop_log_scale (mcmc.js:538-550), a follow-on kernel -----------------------
+struct AdaptArgs {
+  int c0, n;
+  double delta[kAdaptChunk];        // min(max_adaptation, initial_adaptation / sqrt(batch_count))
+  double batch_size[kAdaptChunk];
+  double target[kAdaptChunk];
+  unsigned char apply[kAdaptChunk];
+};
+
+__global__ void __launch_bounds__(256) amwg_adapt_kernel(ChainArrays a, AdaptArgs ad) {
+  unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= a.C) return;
+  for (int k = 0; k < ad.n; ++k) {
+    if (!ad.apply[k]) continue;
+    unsigned long long idx = (unsigned long long)(ad.c0 + k) * a.C + chain;
+    double rate = (double)a.acc[idx] / ad.batch_size[k];
+    double ls = a.pls[idx];
+    a.pls[idx] = (rate > ad.target[k]) ? ls + ad.delta[k] : ls - ad.delta[k];
+    a.acc[idx] = 0;
+  }
+}
+
+// ---- derived quantities for amwg_get_state ------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) amwg_derived_kernel(ModelDev m, ChainArrays a, double* out /*[n_derived][C]*/) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+  unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (chain >= a.C) return;
+  double der[kMaxDerived];
+  EvalState es{a.state + chain, a.C, -1, 0.0};
+  eval_derived(ctx, es, m.derived_prog, der);
+  for (int d = 0; d < m.n_derived; ++d) out[(unsigned long long)d * a.C + chain] = der[d];
+}
+
+// ---- primitives for the parity tests ---------------------------------------------------------------------------------------
+__global__ void amwg_ld_kernel(int op, const double* __restrict__ args, int arity, long long n, double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double stk[kStack];
+  int sp = 0;
+  for (int k = 0; k < arity; ++k) stk[sp++] = args[i * arity + k];
+  Ctx ctx{};
+  EvalState es{nullptr, 0, -1, 0.0};
+  int pc = 0;
+  exec_basic(ctx, es, op, 0, pc, stk, sp, 0);
+  out[i] = stk[sp - 1];
+}
+
+__global__ void amwg_primitive_kernel(int kind, const double* __restrict__ x, long long n, unsigned long long seed,
+                                      unsigned long long chain, double* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (kind == 0) out[i] = js_log(x[i]);
+  else if (kind == 1) out[i] = js_exp(x[i]);
+  else if (kind == 2) { RandomStream g; g.init(seed, chain, (unsigned long long)i); out[i] = g.next(); }
+  else if (kind == 3) {   // sequential rnorm(x[0], x[1]) draws of one chain: thread 0 only
+    if (i == 0) { RandomStream g; g.init(seed, chain, 0); for (long long k = 0; k < n; ++k) out[k] = js_rnorm(g, x[0], x[1]); }
+  } else if (kind == 4) out[i] = js_round(x[i]);
+}
+
+}  // namespace amwg
+
+// ===================================================================================================================
+// Host side: the C ABI
+// ===================================================================================================================
+using namespace amwg;
+
+static thread_local std::string g_last_error;
+static int fail(const std::string& msg) { g_last_error = msg; return -1; }
+#define CUDA_TRY(expr)                                                                                 \
+  do {                                                                                                 \
+    cudaError_t _e = (expr);                                                                           \
+    if (_e != cudaSuccess) return fail(std::string(#expr) + ": " + cudaGetErrorString(_e));           \
+  } while (0)
+
+struct amwg_sampler {
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  ModelDev m{};
+  ChainArrays a{};
+  unsigned smem_bytes = 0;
+  int D = 0, P = 0, n_derived = 0;
+  std::vector<amwg_param> params;
+  std::vector<amwg_comp_options> opts;
+  std::vector<int> comp_type;                 // per component: AMWG_REAL/INT/BINARY
+  std::vector<unsigned char> is_adapting;     // per component (host mirror of m.adapting)
+  std::vector<double> iter_since, batch_count;   // chain-invariant counters (mcmc.js:510-511)
+  std::vector<void*> dev_allocs;
+  unsigned char* d_adapting = nullptr;
+  double* d_out = nullptr; size_t d_out_bytes = 0;
+  int* d_monitor = nullptr; int d_monitor_cap = 0;
+  long long launches = 0;
+  double last_sweep_ms = 0.0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+};
+
+template <typename T>
+static int dev_upload(amwg_sampler* s, const T* host, size_t n, T** out, size_t pad_to = 16) {
+  size_t bytes = std::max<size_t>(((n * sizeof(T) + pad_to - 1) / pad_to) * pad_to, pad_to);
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, bytes));
+  s->dev_allocs.push_back(p);
+  CUDA_TRY(cudaMemsetAsync(p, 0, bytes, s->stream));
+  if (n) CUDA_TRY(cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+template <typename T>
+static int dev_alloc(amwg_sampler* s, size_t n, T** out) {
+  void* p = nullptr;
+  CUDA_TRY(cudaMalloc(&p, std::max<size_t>(n * sizeof(T), 16)));
+  s->dev_allocs.push_back(p);
+  *out = reinterpret_cast<T*>(p);
+  return 0;
+}
+
+static unsigned pad16(size_t b) { return (unsigned)((b + 15) / 16 * 16); }
+
+static int validate_model(const amwg_model* md) {
+  if (!md) return fail("amwg_create: model is NULL");
+  if (md->abi_version != AMWG_ABI_VERSION) return fail("amwg_create: ABI version mismatch");
+  if (md->n_params < 1 || md->n_params > kMaxParams) return fail("amwg_create: between 1 and 16 named parameters are supported");
+  if (md->n_columns > kMaxColumns) return fail("amwg_create: at most 16 data columns are supported");
+  if (md->n_derived > kMaxDerived) return fail("amwg_create: at most 8 derived quantities are supported");
+  int D = 0;
+  for (int p = 0; p < md->n_params; ++p) {
+    const amwg_param& pa = md->params[p];
+    if (pa.lower > pa.upper) return fail("Can not initialize parameter where lower bound > upper bound");   // mcmc.js:314-316
+    if (pa.type < 0 || pa.type > 2) return fail("AmwgStepper can't handle parameter with this type");        // mcmc.js:867
+    if (pa.n_comp < 1 || pa.dim0 < 1 || pa.n_comp % pa.dim0) return fail("amwg_create: bad parameter dimensions");
+    if (pa.dim0 > kMaxDim0) return fail("amwg_create: dim[0] > 256 is not supported");
+    if (pa.comp_offset != D) return fail("amwg_create: comp_offset must be the running component count");
+    if (pa.type == AMWG_BINARY)
+      for (int c = 0; c < pa.n_comp; ++c)
+        if (md->init[D + c] != 0.0 && md->init[D + c] != 1.0) return fail("amwg_create: binary parameters must start at 0 or 1");
+    D += pa.n_comp;
+  }
+  if (D != md->n_comp) return fail("amwg_create: n_comp does not match the parameter list");
+  if (md->logpost_prog < 0 || md->logpost_prog >= md->n_code) return fail("amwg_create: logpost_prog out of range");
+  if (md->n_derived > 0 && (md->derived_prog < 0 || md->derived_prog >= md->n_code)) return fail("amwg_create: derived_prog out of range");
+  return 0;
+}
+
+extern "C" int amwg_abi_version(void) { return AMWG_ABI_VERSION; }
+extern "C" const char* amwg_last_error(void) { return g_last_error.c_str(); }
+extern "C" int64_t amwg_kernel_launches(const amwg_sampler* s) { return s ? s->launches : 0; }
+extern "C" double amwg_last_sweep_kernel_ms(const amwg_sampler* s) { return s ? s->last_sweep_ms : 0.0; }
+extern "C" uint64_t amwg_n_chains(const amwg_sampler* s) { return s ? s->a.C : 0; }
+
+extern "C" void amwg_destroy(amwg_sampler* s) {
+  if (!s) return;
+  cudaSetDevice(s->device);
+  if (s->stream) cudaStreamSynchronize(s->stream);
+  if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+  for (void* p : s->dev_allocs) cudaFree(p);
+  if (s->d_out) cudaFree(s->d_out);
+  if (s->d_monitor) cudaFree(s->d_monitor);
+  for (auto& e : s->ev_pool) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+  if (s->stream) cudaStreamDestroy(s->stream);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  delete s;
+}
+
+static unsigned grid_for(unsigned long long C, int threads) { return (unsigned)((C + threads - 1) / threads); }
+
+extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t first_chain, uint64_t seed, int device,
+                           amwg_sampler** out) {
+  if (!out) return fail("amwg_create: out is NULL");
+  *out = nullptr;
+  if (validate_model(md)) return -1;
+  if (n_chains == 0) return fail("amwg_create: n_chains must be > 0");
+  int ndev = 0;
+  CUDA_TRY(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail("amwg_create: no such CUDA device (this library has no CPU fallback)");
+  CUDA_TRY(cudaSetDevice(device));
+  amwg_sampler* s = new amwg_sampler();
+  s->device = device;
+  auto bail = [&](int rc) { amwg_destroy(s); return rc; };
+  if (cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+  if (cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail("cudaStreamCreate failed"));
+
+  s->D = md->n_comp; s->P = md->n_params; s->n_derived = md->n_derived;
+  s->params.assign(md->params, md->params + md->n_params);
+  s->opts.assign(md->comp_options, md->comp_options + md->n_comp);
+  s->comp_type.resize(s->D);
+  for (const auto& pa : s->params) for (int c = 0; c < pa.n_comp; ++c) s->comp_type[pa.comp_offset + c] = pa.type;
+  s->is_adapting.resize(s->D);
+  for (int c = 0; c < s->D; ++c) s->is_adapting[c] = (s->comp_type[c] != AMWG_BINARY && s->opts[c].is_adapting) ? 1 : 0;
+  s->iter_since.assign(s->D, 0.0);
+  s->batch_count.assign(s->D, 0.0);
+
+  // model image: [code | consts | plates | params], 16B-aligned sections, one bulk-TMA transfer per CTA
+  ModelDev& m = s->m;
+  std::vector<unsigned char> image;
+  auto append = [&](const void* p, size_t bytes) { unsigned off = (unsigned)image.size(); image.resize(off + pad16(std::max<size_t>(bytes, 1)), 0); if (bytes) memcpy(image.data() + off, p, bytes); return off; };
+  m.off_code = append(md->code, sizeof(int32_t) * (size_t)md->n_code);
+  m.off_consts = append(md->consts, sizeof(double) * (size_t)md->n_consts);
+  m.off_plates = append(md->plates, sizeof(amwg_plate) * (size_t)md->n_plates);
+  m.off_params = append(md->params, sizeof(amwg_param) * (size_t)md->n_params);
+  m.image_bytes = (unsigned)image.size();
+  unsigned char* d_image = nullptr;
+  if (dev_upload(s, image.data(), image.size(), &d_image)) return bail(-1);
+  m.image = d_image;
+  m.n_columns = md->n_columns; m.n_plates = md->n_plates; m.n_params = md->n_params; m.D = md->n_comp;
+  m.n_derived = md->n_derived; m.logpost_prog = md->logpost_prog; m.derived_prog = md->derived_prog;
+
+  unsigned smem_used = m.image_bytes;
+  for (int k = 0; k < md->n_columns; ++k) {
+    double* d_col = nullptr;
+    if (dev_upload(s, md->columns[k].values, (size_t)md->columns[k].n, &d_col)) return bail(-1);
+    m.col_global[k] = d_col;
+    m.col_bytes[k] = pad16(std::max<size_t>(sizeof(double) * (size_t)md->columns[k].n, 16));
+    if (smem_used + m.col_bytes[k] <= kSmemBudget) { m.col_smem_off[k] = (int)smem_used; smem_used += m.col_bytes[k]; }
+    else m.col_smem_off[k] = -1;       // too large for shared memory: served from L2 (streamed tiles: DESIGN.md "next")
+  }
+  s->smem_bytes = smem_used;
+  if (cudaFuncSetAttribute(amwg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
+    return bail(fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
+
+  if (dev_upload(s, s->is_adapting.data(), (size_t)s->D, &s->d_adapting)) return bail(-1);
+  m.adapting = s->d_adapting;
+
+  ChainArrays& a = s->a;
+  a.C = n_chains; a.first_chain = first_chain; a.seed = seed;
+  size_t DC = (size_t)s->D * (size_t)n_chains;
+  if (dev_alloc(s, DC, &a.state) || dev_alloc(s, DC, &a.pls) || dev_alloc(s, DC, &a.acc) || dev_alloc(s, (size_t)n_chains, &a.curr_lp) ||
+      dev_alloc(s, (size_t)n_chains, &a.perm) || dev_alloc(s, (size_t)n_chains, &a.rng_n))
+    return bail(-1);
+
+  double* d_init = nullptr; double* d_pls0 = nullptr;
+  std::vector<double> pls0(s->D);
+  for (int c = 0; c < s->D; ++c) pls0[c] = s->opts[c].prop_log_scale;
+  if (dev_upload(s, md->init, (size_t)s->D, &d_init) || dev_upload(s, pls0.data(), (size_t)s->D, &d_pls0)) return bail(-1);
+
+  amwg_init_kernel<<<grid_for(n_chains, kThreads), kThreads, s->smem_bytes, s->stream>>>(m, a, d_init, d_pls0);
+  s->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+  if (e != cudaSuccess) return bail(fail(std::string("amwg_init_kernel: ") + cudaGetErrorString(e)));
+  *out = s;
+  return 0;
+}
+
+// Run n Sampler.step()s. Between sweep launches the host advances the chain-invariant adaptation counters and, when a
+// component reaches its batch boundary (mcmc.js:538), launches the adaptation kernel. A launch never crosses a boundary.
+static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, const int* d_monitor, int n_monitor, double* d_out,
+                      double* host_out) {
+  const unsigned long long C = s->a.C;
+  long long i0 = 0;
+  size_t n_events = 0;
+  long long rows_copied = 0;
+  while (i0 < n) {
+    long long L = n - i0;
+    for (int c = 0; c < s->D; ++c) {
+      if (!s->is_adapting[c]) continue;
+      double need = std::ceil(s->opts[c].batch_size - s->iter_since[c]);
+      if (!(need >= 1.0)) need = 1.0;
+      if (need < (double)L) L = (long long)need;
+    }
+    SweepArgs sa{L, i0, thin, record, n_monitor, d_monitor, d_out};
+    if (n_events >= s->ev_pool.size()) {
+      cudaEvent_t e0, e1;
+      CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+      s->ev_pool.emplace_back(e0, e1);
+    }
+    CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].first, s->stream));
+    amwg_sweep_kernel<<<grid_for(C, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].second, s->stream));
+    n_events++;
+    s->launches++;
+
+    // chain-invariant bookkeeping of OnedimMetropolisStepper (mcmc.js:536-551)
+    bool any = false;
+    std::vector<unsigned char> apply(s->D, 0);
+    std::vector<double> delta(s->D, 0.0);
+    for (int c = 0; c < s->D; ++c) {
+      if (!s->is_adapting[c]) continue;
+      s->iter_since[c] += (double)L;
+      if (s->iter_since[c] >= s->opts[c].batch_size) {
+        s->batch_count[c] += 1.0;
+        double adj = s->opts[c].initial_adaptation / std::sqrt(s->batch_count[c]);
+        double mx = s->opts[c].max_adaptation;
+        delta[c] = (adj != adj || mx != mx) ? NAN : std::min(mx, adj);
+        apply[c] = 1; any = true;
+        s->iter_since[c] = 0.0;
+      }
+    }
+    if (any) {
+      for (int c0 = 0; c0 < s->D; c0 += kAdaptChunk) {
+        AdaptArgs ad{};
+        ad.c0 = c0; ad.n = std::min(kAdaptChunk, s->D - c0);
+        bool chunk_any = false;
+        for (int k = 0; k < ad.n; ++k) {
+          ad.apply[k] = apply[c0 + k]; ad.delta[k] = delta[c0 + k];
+          ad.batch_size[k] = s->opts[c0 + k].batch_size; ad.target[k] = s->opts[c0 + k].target_accept_rate;
+          chunk_any |= (apply[c0 + k] != 0);
+        }
+        if (!chunk_any) continue;
+        amwg_adapt_kernel<<<grid_for(C, 256), 256, 0, s->stream>>>(s->a, ad);
+        CUDA_TRY(cudaGetLastError());
+        s->launches++;
+      }
+    }
+    i0 += L;
+    // rows [rows_copied, rows_done) are final: overlap their D2H with the next sweeps
+    if (record && host_out) {
+      long long rows_done = (i0 + thin - 1) / thin;
+      if (rows_done > rows_copied) {
+        cudaEvent_t done = s->ev_pool[n_events - 1].second;
+        CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, done, 0));
+        size_t row_elems = (size_t)n_monitor * (size_t)C;
+        CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)rows_copied * row_elems, d_out + (size_t)rows_copied * row_elems,
+                                 (size_t)(rows_done - rows_copied) * row_elems * sizeof(double), cudaMemcpyDeviceToHost, s->copy_stream));
+        rows_copied = rows_done;
+      }
+    }
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  if (record && host_out) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+  double ms = 0.0;
+  for (size_t k = 0; k < n_events; ++k) {
+    float t = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&t, s->ev_pool[k].first, s->ev_pool[k].second));
+    ms += t;
+  }
+  s->last_sweep_ms = ms;
+  return 0;
+}
+
+extern "C" int amwg_burn(amwg_sampler* s, int64_t n) {
+  if (!s) return fail("amwg_burn: NULL handle");
+  if (n < 0) return fail("amwg_burn: n must be >= 0");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (n == 0) { s->last_sweep_ms = 0.0; return 0; }
+  return run_sweeps(s, n, 0, 1, nullptr, 0, nullptr, nullptr);
+}
+
+static int prepare_monitor(amwg_sampler* s, const int32_t* monitor, int32_t n_monitor) {
+  if (n_monitor < 0 || (n_monitor > 0 && !monitor)) return fail("amwg_sample: bad monitor list");
+  for (int j = 0; j < n_monitor; ++j)
+    if (monitor[j] < 0 || monitor[j] >= s->D + s->n_derived) return fail("amwg_sample: monitor entry out of range");
+  if (n_monitor > s->d_monitor_cap) {
+    if (s->d_monitor) cudaFree(s->d_monitor);
+    s->d_monitor = nullptr; s->d_monitor_cap = 0;
+    CUDA_TRY(cudaMalloc(&s->d_monitor, sizeof(int) * (size_t)std::max(n_monitor, 16)));
+    s->d_monitor_cap = std::max(n_monitor, 16);
+  }
+  if (n_monitor) CUDA_TRY(cudaMemcpyAsync(s->d_monitor, monitor, sizeof(int) * (size_t)n_monitor, cudaMemcpyHostToDevice, s->stream));
+  return 0;
+}
+
+extern "C" int amwg_sample_device(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* dev_out) {
+  if (!s) return fail("amwg_sample: NULL handle");
+  if (n < 0 || thin < 1) return fail("amwg_sample: n must be >= 0 and thin >= 1");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (prepare_monitor(s, monitor, n_monitor)) return -1;
+  if (n == 0) { s->last_sweep_ms = 0.0; return 0; }
+  if (n_monitor > 0 && !dev_out) return fail("amwg_sample_device: dev_out is NULL");
+  return run_sweeps(s, n, 1, thin, s->d_monitor, n_monitor, dev_out, nullptr);
+}
+
+extern "C" int amwg_sample(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* host_out) {
+  if (!s) return fail("amwg_sample: NULL handle");
+  if (n < 0 || thin < 1) return fail("amwg_sample: n must be >= 0 and thin >= 1");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (prepare_monitor(s, monitor, n_monitor)) return -1;
+  if (n == 0) { s->last_sweep_ms = 0.0; return 0; }
+  if (n_monitor > 0 && !host_out) return fail("amwg_sample: host_out is NULL");
+  size_t rows = (size_t)((n + thin - 1) / thin);
+  size_t bytes = rows * (size_t)n_monitor * (size_t)s->a.C * sizeof(double);
+  if (bytes > s->d_out_bytes) {
+    if (s->d_out) cudaFree(s->d_out);
+    s->d_out = nullptr; s->d_out_bytes = 0;
+    CUDA_TRY(cudaMalloc(&s->d_out, std::max<size_t>(bytes, 16)));
+    s->d_out_bytes = bytes;
+  }
+  return run_sweeps(s, n, 1, thin, s->d_monitor, n_monitor, s->d_out, host_out);
+}
+
+extern "C" int amwg_get_state(amwg_sampler* s, double* host_out) {
+  if (!s || !host_out) return fail("amwg_get_state: NULL argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  size_t C = (size_t)s->a.C;
+  CUDA_TRY(cudaMemcpyAsync(host_out, s->a.state, sizeof(double) * (size_t)s->D * C, cudaMemcpyDeviceToHost, s->stream));
+  if (s->n_derived > 0) {
+    double* d_der = nullptr;
+    CUDA_TRY(cudaMalloc(&d_der, sizeof(double) * (size_t)s->n_derived * C));
+    amwg_derived_kernel<<<grid_for(C, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, d_der);
+    s->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host_out + (size_t)s->D * C, d_der, sizeof(double) * (size_t)s->n_derived * C, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(d_der);
+    if (e != cudaSuccess) return fail(std::string("amwg_get_state: ") + cudaGetErrorString(e));
+    return 0;
+  }
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int amwg_set_adapting(amwg_sampler* s, int32_t flag) {
+  if (!s) return fail("amwg_set_adapting: NULL handle");
+  CUDA_TRY(cudaSetDevice(s->device));
+  for (int c = 0; c < s->D; ++c) s->is_adapting[c] = (s->comp_type[c] != AMWG_BINARY && flag) ? 1 : 0;
+  CUDA_TRY(cudaMemcpyAsync(s->d_adapting, s->is_adapting.data(), (size_t)s->D, cudaMemcpyHostToDevice, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scale, int32_t* acceptance_count) {
+  if (!s) return fail("amwg_info: NULL handle");
+  CUDA_TRY(cudaSetDevice(s->device));
+  if (scalars)
+    for (int c = 0; c < s->D; ++c) {
+      scalars[c * 3 + 0] = s->is_adapting[c]; scalars[c * 3 + 1] = s->iter_since[c]; scalars[c * 3 + 2] = s->batch_count[c];
+    }
+  size_t DC = (size_t)s->D * (size_t)s->a.C;
+  if (prop_log_scale) CUDA_TRY(cudaMemcpyAsync(prop_log_scale, s->a.pls, sizeof(double) * DC, cudaMemcpyDeviceToHost, s->stream));
+  if (acceptance_count) CUDA_TRY(cudaMemcpyAsync(acceptance_count, s->a.acc, sizeof(int) * DC, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+extern "C" int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device) {
+  if (n <= 0) return 0;
+  if (op <= AMWG_OP_END || op >= AMWG_OP_ACC || arity < 1 || arity > 4) return fail("amwg_ld_eval: bad opcode or arity");
+  CUDA_TRY(cudaSetDevice(device));
+  double *d_args = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_args, sizeof(double) * (size_t)n * arity));
+  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(d_args); return fail("amwg_ld_eval: cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(d_args, args, sizeof(double) * (size_t)n * arity, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    amwg_ld_kernel<<<(unsigned)((n + 127) / 128), 128>>>(op, d_args, arity, n, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_args); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(std::string("amwg_ld_eval: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device) {
+  if (n <= 0) return 0;
+  CUDA_TRY(cudaSetDevice(device));
+  double *d_x = nullptr, *d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_x, sizeof(double) * (size_t)n));
+  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(d_x); return fail("amwg_primitive_eval: cudaMalloc failed"); }
+  cudaError_t e = cudaMemcpy(d_x, x, sizeof(double) * (size_t)n, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) {
+    amwg_primitive_kernel<<<(unsigned)((n + 127) / 128), 128>>>(kind, d_x, n, seed, chain, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
+  cudaFree(d_x); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(std::string("amwg_primitive_eval: ") + cudaGetErrorString(e));
+  return 0;
+}

@@ -1,0 +1,75 @@
+"""Multi-GPU plumbing: one process per GPU (torch.distributed), chains sharded, no data-path collective.
+
+Chains are independent (the reference runs exactly one, mcmc.js:940-966), so the path shards embarrassingly: rank r
+owns the contiguous block of global chain ids [r*C/G, (r+1)*C/G).  The Philox stream is keyed by the GLOBAL chain id,
+so the draws do not depend on G.  The only collective is the final all-gather of the sample blocks in `sample()`
+(NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Tuple
+
+import numpy as np
+
+
+def world() -> Tuple[int, int]:
+    """(rank, world_size) from torch.distributed if initialised, else from the torchrun environment."""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+    except Exception:
+        pass
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def shard_bounds(n_chains: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous block of rank `rank`: (first_chain, count). Remainder chains go to the lowest ranks."""
+    base, rem = divmod(int(n_chains), int(world_size))
+    first = rank * base + min(rank, rem)
+    return first, base + (1 if rank < rem else 0)
+
+
+def shard_chains(n_chains: int) -> Tuple[int, int]:
+    rank, ws = world()
+    return shard_bounds(n_chains, rank, ws)
+
+
+def all_gather_chain_axis(local, counts):
+    """All-gather tensors that differ only in their last (chain) axis. `counts[r]` = chains of rank r.
+    Works for CUDA tensors over NCCL and CPU tensors over gloo."""
+    import torch
+    import torch.distributed as dist
+    ws = dist.get_world_size()
+    if len(set(counts)) == 1:
+        # equal blocks: one all_gather_into_tensor over a [ws, rows, entries, c] buffer
+        out = torch.empty((ws,) + tuple(local.shape), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous())
+        return torch.cat(list(out.unbind(0)), dim=-1)
+    parts = [torch.empty(tuple(local.shape[:-1]) + (c,), dtype=local.dtype, device=local.device) for c in counts]
+    dist.all_gather(parts, local.contiguous())
+    return torch.cat(parts, dim=-1)
+
+
+def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) -> np.ndarray:
+    """sample() on this rank's shard into a device buffer, all-gather over the chain axis, then D2H.
+    Returns [rows, n_entries, total_chains] on every rank."""
+    import torch
+    import torch.distributed as dist
+    from . import _ffi
+    from .tracer import JsThrow
+    if not (dist.is_available() and dist.is_initialized()):
+        raise JsThrow("options.distributed needs an initialised torch.distributed process group")
+    L = _ffi.lib()
+    dev = torch.device("cuda", sampler.device)
+    local = torch.empty((rows, len(mon), sampler.local_chains), dtype=torch.float64, device=dev)
+    torch.cuda.synchronize(dev)
+    rc = L.amwg_sample_device(sampler._handle, n, thin, mon.ctypes.data_as(C.POINTER(C.c_int32)), len(mon), local.data_ptr())
+    if rc != 0:
+        raise JsThrow(L.amwg_last_error().decode())
+    ws = dist.get_world_size()
+    counts = [shard_bounds(sampler.n_chains, r, ws)[1] for r in range(ws)]
+    full = all_gather_chain_axis(local, counts)
+    return full.cpu().numpy()

@@ -1,0 +1,723 @@
+"""Turn a ``log_post(state, data)`` closure into the program the CUDA sampler runs.
+
+The reference calls an opaque JS closure twice per parameter step (mcmc.js:958-960, 524-526).  A GPU
+cannot call back into the host per step, so the closure is executed ONCE here with symbolic
+parameter values and proxied data; what it computes is recorded as an expression, then lowered to
+the postfix program of include/amwg.h:
+
+* the returned value is split along its left spine of ``+`` into terms, preserving the order of the
+  user's ``log_post += ...`` statements (so the device forms the sum in the JS order);
+* runs of structurally identical terms that walk through the data (``for i: log_post +=
+  ld.norm(data[i], mu, sigma)``) become *plates*; recognised plate bodies get a hand-written
+  inner loop (AMWG_PLATE_*), anything else is interpreted per point;
+* keys the closure adds to ``state`` (``par.var = sigma*sigma``, tests/test_data.js:89) become
+  derived quantities.
+
+Python control flow on a symbolic value cannot be traced (``if m == 0`` with a parameter m): use
+``where(cond, a, b)``.  Such closures raise ``JsThrow`` -- there is no CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import numbers
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from ._ffi import (OP, PLATE_BERN_IID, PLATE_GENERIC, PLATE_NORM_GROUPED, PLATE_NORM_IID, PLATE_POIS_LOGLIN)
+
+
+class JsThrow(Exception):
+    """The reference throws bare strings (``throw "..."``); Python needs an exception type.
+    ``str(e)`` / ``e.message`` is exactly the string the reference would throw."""
+
+    def __init__(self, message: str):
+        super().__init__(message)
+        self.message = message
+
+
+# ------------------------------------------------------------------------------------------------
+# symbolic values
+# ------------------------------------------------------------------------------------------------
+class Sym:
+    """A node of the recorded expression. ``op`` is an opcode name of include/amwg.h."""
+    __slots__ = ("op", "args", "val")
+
+    def __init__(self, op: str, args: tuple = (), val: Any = None):
+        self.op = op
+        self.args = args
+        self.val = val
+
+    # arithmetic: one IEEE operation per node, like the JS operator it mirrors
+    def __add__(self, o): return Sym("ADD", (self, lift(o)))
+    def __radd__(self, o): return Sym("ADD", (lift(o), self))
+    def __sub__(self, o): return Sym("SUB", (self, lift(o)))
+    def __rsub__(self, o): return Sym("SUB", (lift(o), self))
+    def __mul__(self, o): return Sym("MUL", (self, lift(o)))
+    def __rmul__(self, o): return Sym("MUL", (lift(o), self))
+    def __truediv__(self, o): return Sym("DIV", (self, lift(o)))
+    def __rtruediv__(self, o): return Sym("DIV", (lift(o), self))
+    def __pow__(self, o): return Sym("POW", (self, lift(o)))
+    def __rpow__(self, o): return Sym("POW", (lift(o), self))
+    def __neg__(self): return Sym("NEG", (self,))
+    def __pos__(self): return self
+    def __abs__(self): return Sym("ABS", (self,))
+    def __lt__(self, o): return Sym("LT", (self, lift(o)))
+    def __le__(self, o): return Sym("LE", (self, lift(o)))
+    def __gt__(self, o): return Sym("GT", (self, lift(o)))
+    def __ge__(self, o): return Sym("GE", (self, lift(o)))
+    def __eq__(self, o): return Sym("EQ", (self, lift(o)))   # noqa: E721  (symbolic comparison)
+    def __ne__(self, o): return Sym("NE", (self, lift(o)))
+    __hash__ = object.__hash__
+
+    def __bool__(self):
+        raise JsThrow("log_post branches on a parameter value, which cannot be traced for the device; "
+                      "use mcmc.where(cond, a, b)")
+
+    def __float__(self):
+        raise JsThrow("log_post converts a parameter to a Python float (e.g. math.log); use mcmc.Math.* / ld.*")
+
+    def __repr__(self):
+        if self.op == "CONST": return f"{self.val!r}"
+        if self.op in ("COMP", "DATA", "DATA_I", "COMP_I"): return f"{self.op}{self.val}"
+        return f"{self.op}({', '.join(map(repr, self.args))})"
+
+
+def lift(x) -> Sym:
+    if isinstance(x, Sym):
+        return x
+    if isinstance(x, (bool, np.bool_)):
+        return Sym("CONST", (), 1.0 if x else 0.0)
+    if isinstance(x, numbers.Real):
+        return Sym("CONST", (), float(x))
+    raise JsThrow(f"log_post produced a value of type {type(x).__name__} that is not a number")
+
+
+def is_sym(x) -> bool:
+    return isinstance(x, Sym)
+
+
+def where(cond, a, b):
+    """``cond ? a : b`` with both branches evaluated (device SELECT)."""
+    if not is_sym(cond) and not is_sym(a) and not is_sym(b):
+        return a if cond else b
+    return Sym("SELECT", (lift(cond), lift(a), lift(b)))
+
+
+def _unary(op):
+    def f(x):
+        return Sym(op, (lift(x),))
+    return f
+
+
+class _Math:
+    """``Math.*`` for use inside log_post: symbolic in, symbolic out (evaluated on the device with JS semantics)."""
+    PI = 3.141592653589793
+    E = 2.718281828459045
+    log = staticmethod(_unary("LOG"))
+    exp = staticmethod(_unary("EXP"))
+    sqrt = staticmethod(_unary("SQRT"))
+    abs = staticmethod(_unary("ABS"))
+
+    @staticmethod
+    def pow(x, y): return Sym("POW", (lift(x), lift(y)))
+
+    @staticmethod
+    def max(a, b): return where(lift(a) > lift(b), a, b)
+
+    @staticmethod
+    def min(a, b): return where(lift(a) < lift(b), a, b)
+
+
+Math = _Math()
+
+
+# ------------------------------------------------------------------------------------------------
+# proxies handed to the closure
+# ------------------------------------------------------------------------------------------------
+class PlateIndex:
+    """Symbolic loop index: ``for i in mcmc.points(n): log_post += ld.norm(data[i], mu, sigma)``
+    records the body once for all n points (the concrete ``for i in range(n)`` form is traced point by
+    point and compressed afterwards; both give the same program)."""
+    __slots__ = ("n", "plate_id")
+
+    def __init__(self, n: int, plate_id: int):
+        self.n = int(n)
+        self.plate_id = plate_id
+
+
+class _Points:
+    def __init__(self, tracer: "Tracer", n: int):
+        self.tracer, self.n = tracer, int(n)
+
+    def __iter__(self):
+        if self.n > 0:
+            yield self.tracer.new_plate_index(self.n)
+
+
+class DataVec:
+    """A 1-D or nested numeric array from ``data``. Elements stay symbolic references into a device column."""
+
+    def __init__(self, tracer: "Tracer", col: int, shape: Tuple[int, ...], offset: int = 0):
+        self._t, self._col, self._shape, self._off = tracer, col, tuple(shape), offset
+
+    def __len__(self): return self._shape[0]
+
+    @property
+    def length(self): return self._shape[0]        # JS spelling
+
+    def _inner(self) -> int:
+        n = 1
+        for d in self._shape[1:]: n *= d
+        return n
+
+    def __getitem__(self, i):
+        inner = self._inner()
+        if isinstance(i, PlateIndex):
+            if i.n != self._shape[0] and len(self._shape) == 1 and i.n > self._shape[0]:
+                raise JsThrow("plate index runs past the end of a data array")
+            if len(self._shape) == 1:
+                return Sym("DATA_I", (), (self._col, self._off, 1, i.plate_id))
+            return _DataRowI(self._t, self._col, self._shape[1:], self._off, inner, i.plate_id)
+        if isinstance(i, Sym):
+            raise JsThrow("indexing data by a parameter value is not supported on the device")
+        i = int(i)
+        if i < 0: i += self._shape[0]
+        if not 0 <= i < self._shape[0]:
+            return Sym("CONST", (), float("nan"))          # JS: undefined -> NaN in arithmetic
+        if len(self._shape) == 1:
+            return Sym("DATA", (), (self._col, self._off + i))
+        return DataVec(self._t, self._col, self._shape[1:], self._off + i * inner)
+
+    def __iter__(self):
+        for i in range(self._shape[0]):
+            yield self[i]
+
+    def value(self, i: int) -> float:
+        return float(self._t.columns[self._col][self._off + i])
+
+
+class _DataRowI:
+    """``data.X[i]`` with a symbolic i: row of a 2-D array."""
+
+    def __init__(self, tracer, col, shape, off, row_stride, plate_id):
+        self._t, self._col, self._shape, self._off, self._rs, self._pid = tracer, col, tuple(shape), off, row_stride, plate_id
+
+    def __len__(self): return self._shape[0]
+
+    def __getitem__(self, k):
+        if len(self._shape) != 1:
+            raise JsThrow("data arrays deeper than 2 levels under a plate index are not supported")
+        k = int(k)
+        return Sym("DATA_I", (), (self._col, self._off + k, self._rs, self._pid))
+
+    def __iter__(self):
+        for k in range(self._shape[0]):
+            yield self[k]
+
+
+class ParamVec:
+    """State of a multi-dim parameter: nested, indexable by ints, by data values and by plate-indexed data."""
+
+    def __init__(self, tracer: "Tracer", comp0: int, shape: Tuple[int, ...]):
+        self._t, self._c0, self._shape = tracer, comp0, tuple(shape)
+
+    def __len__(self): return self._shape[0]
+
+    @property
+    def length(self): return self._shape[0]
+
+    def __getitem__(self, i):
+        inner = 1
+        for d in self._shape[1:]: inner *= d
+        if isinstance(i, Sym):
+            if i.op == "DATA":                      # concrete data value used as an index (mu[g[i]])
+                i = int(self._t.columns[i.val[0]][i.val[1]])
+            elif i.op == "DATA_I" and len(self._shape) == 1:
+                col, off, stride, pid = i.val
+                return Sym("COMP_I", (), (col, off, stride, self._c0, pid))
+            else:
+                raise JsThrow("a parameter array can only be indexed by numbers or by data values")
+        i = int(i)
+        if i < 0: i += self._shape[0]
+        if not 0 <= i < self._shape[0]:
+            return Sym("CONST", (), float("nan"))
+        if len(self._shape) == 1:
+            return Sym("COMP", (), self._c0 + i)
+        return ParamVec(self._t, self._c0 + i * inner, self._shape[1:])
+
+    def __iter__(self):
+        for i in range(self._shape[0]):
+            yield self[i]
+
+
+class State(dict):
+    """``state``: parameters by name, attribute or item access (``state.mu`` / ``state["mu"]``).
+    Keys the closure adds are derived quantities (mcmc.js:961-963)."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+class DataObject(dict):
+    """``data`` when it is an object: attribute and item access."""
+
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+
+# ------------------------------------------------------------------------------------------------
+# tracing + lowering
+# ------------------------------------------------------------------------------------------------
+_MIN_PLATE = 8          # shorter runs stay unrolled scalar terms
+_ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, "SQRT": 1, "ABS": 1, "POW": 2,
+          "LT": 2, "LE": 2, "GT": 2, "GE": 2, "EQ": 2, "NE": 2, "AND": 2, "OR": 2, "NOT": 1, "SELECT": 3,
+          "LGAMMA": 1, "LFACTORIAL": 1, "LCHOOSE": 2, "LBETA": 2,
+          "LD_NORM": 3, "LD_UNIF": 3, "LD_BETA": 3, "LD_BERN": 2, "LD_POIS": 2, "LD_CAUCHY": 3, "LD_LAPLACE": 3,
+          "LD_GAMMA": 3, "LD_INVGAMMA": 3, "LD_LNORM": 3, "LD_PARETO": 3, "LD_T": 4, "LD_WEIBULL": 3, "LD_LOGIS": 3,
+          "LD_EXP": 2, "LD_BINOM": 3, "LD_NBINOM": 3, "LD_HYPER": 4}
+
+
+class Program:
+    """The lowered model: everything amwg_model needs, as numpy arrays."""
+
+    def __init__(self):
+        self.code: List[int] = []
+        self.consts: List[float] = []
+        self._const_index: Dict[bytes, int] = {}
+        self.columns: List[np.ndarray] = []
+        self.plates: List[dict] = []
+        self.logpost_prog = 0
+        self.derived_prog = -1
+        self.derived_names: List[str] = []
+        self.summary: List[str] = []           # human-readable: what each term became
+
+    def const(self, v: float) -> int:
+        key = np.float64(v).tobytes()
+        k = self._const_index.get(key)
+        if k is None:
+            k = len(self.consts)
+            self.consts.append(float(v))
+            self._const_index[key] = k
+        return k
+
+    def emit(self, op: str, operand: int = 0, *extra: int):
+        self.code.append((int(operand) << 8) | OP[op])
+        self.code.extend(int(e) for e in extra)
+
+
+class Tracer:
+    def __init__(self):
+        self.columns: List[np.ndarray] = []
+        self._col_ids: Dict[int, int] = {}
+        self._n_plate_idx = 0
+        self.plate_sizes: Dict[int, int] = {}
+
+    # -- data -----------------------------------------------------------------------------------
+    def add_column(self, arr: np.ndarray) -> int:
+        self.columns.append(np.ascontiguousarray(arr, dtype=np.float64).reshape(-1))
+        return len(self.columns) - 1
+
+    def wrap_data(self, data):
+        """Proxy `data` (any nesting of dicts / lists / arrays / numbers; opaque to the reference, mcmc.js:942)."""
+        if data is None or isinstance(data, (str, bytes)):
+            return data
+        if isinstance(data, (bool, numbers.Real)):
+            return float(data)
+        if isinstance(data, dict):
+            return DataObject({k: self.wrap_data(v) for k, v in data.items()})
+        if isinstance(data, (list, tuple, np.ndarray)):
+            try:
+                arr = np.asarray(data, dtype=np.float64)
+            except (ValueError, TypeError):
+                return [self.wrap_data(v) for v in data]          # ragged / mixed: recurse
+            if arr.ndim == 0:
+                return float(arr)
+            if arr.size == 0:
+                return []
+            col = self.add_column(arr)
+            return DataVec(self, col, arr.shape)
+        return data
+
+    def new_plate_index(self, n: int) -> PlateIndex:
+        pid = self._n_plate_idx
+        self._n_plate_idx += 1
+        self.plate_sizes[pid] = int(n)
+        return PlateIndex(n, pid)
+
+    def points(self, n) -> _Points:
+        return _Points(self, int(n))
+
+    # -- state ----------------------------------------------------------------------------------
+    def make_state(self, params: Dict[str, dict], offsets: Dict[str, int]) -> State:
+        st = State()
+        for name, p in params.items():
+            dim = list(p["dim"])
+            if dim == [1]:
+                st[name] = Sym("COMP", (), offsets[name])
+            else:
+                st[name] = ParamVec(self, offsets[name], tuple(dim))
+        return st
+
+
+def _spine_terms(expr: Sym) -> List[Sym]:
+    """((0 + t1) + t2) + ...  ->  [t1, t2, ...] (iterative: spines can be 1e6 deep)."""
+    terms: List[Sym] = []
+    node = expr
+    while node.op == "ADD":
+        terms.append(node.args[1])
+        node = node.args[0]
+    if not (node.op == "CONST" and node.val == 0.0 and terms):
+        terms.append(node)
+    terms.reverse()
+    return terms
+
+
+def _signature(node: Sym, slots: list):
+    """Structure of a term with data positions abstracted; collects (kind, col, index[, base]) per slot."""
+    if node.op == "CONST": return ("K", node.val if node.val == node.val else "nan")
+    if node.op == "COMP": return ("C", node.val)
+    if node.op == "DATA":
+        slots.append(("D", node.val[0], node.val[1]))
+        return ("D", node.val[0])
+    if node.op in ("DATA_I", "COMP_I"):
+        return (node.op, node.val)
+    return (node.op,) + tuple(_signature(a, slots) for a in node.args)
+
+
+def _signature_loose(node: Sym, slots: list):
+    """As _signature, but parameter components are slots too (mu[g[i]] varies from point to point)."""
+    if node.op == "CONST": return ("K", node.val if node.val == node.val else "nan")
+    if node.op == "COMP":
+        slots.append(("C", -1, node.val))
+        return ("C?",)
+    if node.op == "DATA":
+        slots.append(("D", node.val[0], node.val[1]))
+        return ("D", node.val[0])
+    if node.op in ("DATA_I", "COMP_I"):
+        return (node.op, node.val)
+    return (node.op,) + tuple(_signature_loose(a, slots) for a in node.args)
+
+
+def _has_plate_ref(node: Sym) -> Optional[int]:
+    """plate id referenced by a symbolic-index term, or None."""
+    stack = [node]
+    while stack:
+        n = stack.pop()
+        if n.op == "DATA_I": return n.val[3]
+        if n.op == "COMP_I": return n.val[4]
+        stack.extend(n.args)
+    return None
+
+
+def _index_free(node: Sym) -> bool:
+    stack = [node]
+    while stack:
+        n = stack.pop()
+        if n.op in ("DATA_I", "COMP_I"): return False
+        stack.extend(n.args)
+    return True
+
+
+class Lowering:
+    def __init__(self, tracer: Tracer, n_comp: int):
+        self.t = tracer
+        self.n_comp = n_comp
+        self.prog = Program()
+        self.prog.columns = tracer.columns       # shared list: synthesized columns are appended
+
+    # -- expressions ------------------------------------------------------------------------------
+    def emit_expr(self, node: Sym):
+        """Postfix emission, iterative (terms are shallow but plates bodies may hold long dot products)."""
+        p = self.prog
+        work: List[Tuple[Sym, bool]] = [(node, False)]
+        while work:
+            n, done = work.pop()
+            if n.op == "CONST":
+                p.emit("CONST", p.const(n.val)); continue
+            if n.op == "COMP":
+                p.emit("COMP", n.val); continue
+            if n.op == "DATA":
+                p.emit("DATA", n.val[0], n.val[1]); continue
+            if n.op == "DATA_I":
+                p.emit("DATA_I", n.val[0], n.val[1], n.val[2]); continue
+            if n.op == "COMP_I":
+                p.emit("COMP_I", n.val[0], n.val[1], n.val[2], n.val[3]); continue
+            if done:
+                p.emit(n.op); continue
+            if n.op not in _ARITY:
+                raise JsThrow(f"cannot lower operation {n.op}")
+            work.append((n, True))
+            for a in reversed(n.args):
+                work.append((a, False))
+
+    def emit_subprogram(self, node: Sym) -> int:
+        """An END-terminated operand program placed after the main program; returns its word offset."""
+        start = len(self._tail)
+        saved, self.prog.code = self.prog.code, []
+        self.emit_expr(node)
+        self.prog.emit("END")
+        self._tail.extend(self.prog.code)
+        self.prog.code = saved
+        return start                         # relative to tail start; fixed up in finish()
+
+    # -- plates -----------------------------------------------------------------------------------
+    def _make_plate(self, body: Sym, n: int) -> int:
+        """Register a plate for `body` (uses DATA_I/COMP_I with stride/offset) over n points; returns plate id."""
+        p = self.prog
+        pl = dict(kind=PLATE_GENERIC, n=n, col=[-1] * 4, arg_prog=[-1] * 4, iparam=[0] * 4, body_prog=-1)
+
+        def data_i(node, stride=1):
+            return node.op == "DATA_I" and node.val[2] == stride
+
+        # ld.norm(data[i], mean, sd) with index-free mean/sd
+        if body.op == "LD_NORM" and data_i(body.args[0]) and _index_free(body.args[2]):
+            x, mean, sd = body.args
+            if _index_free(mean):
+                pl.update(kind=PLATE_NORM_IID)
+                pl["col"][0] = x.val[0]; pl["iparam"][2] = x.val[1]
+                pl["arg_prog"][0] = self.emit_subprogram(mean)
+                pl["arg_prog"][1] = self.emit_subprogram(sd)
+                p.summary.append(f"plate NORM_IID n={n}")
+            elif mean.op == "COMP_I":
+                grp = self._grouped(mean, n)
+                if grp is not None:
+                    base, J, start_col = grp
+                    pl.update(kind=PLATE_NORM_GROUPED)
+                    pl["col"][0] = x.val[0]; pl["col"][1] = start_col; pl["iparam"][2] = x.val[1]
+                    pl["iparam"][0] = base; pl["iparam"][1] = J
+                    pl["arg_prog"][1] = self.emit_subprogram(sd)
+                    p.summary.append(f"plate NORM_GROUPED n={n} groups={J}")
+        elif body.op == "LD_BERN" and data_i(body.args[0]) and _index_free(body.args[1]):
+            pl.update(kind=PLATE_BERN_IID)
+            pl["col"][0] = body.args[0].val[0]; pl["iparam"][2] = body.args[0].val[1]
+            pl["arg_prog"][0] = self.emit_subprogram(body.args[1])
+            p.summary.append(f"plate BERN_IID n={n}")
+        elif body.op == "LD_POIS" and data_i(body.args[0]) and body.args[1].op == "EXP":
+            lin = self._loglinear(body.args[1].args[0])
+            if lin is not None:
+                xcol, K, base = lin
+                y = body.args[0]
+                ycol = self.t.columns[y.val[0]][y.val[1]: y.val[1] + n]
+                lf = np.array([_lfactorial_host(v) for v in ycol])      # constant in the parameters
+                pl.update(kind=PLATE_POIS_LOGLIN)
+                pl["col"][0] = y.val[0]; pl["iparam"][2] = y.val[1]
+                pl["col"][1] = xcol; pl["col"][2] = self.t.add_column(lf)
+                pl["iparam"][0] = base; pl["iparam"][1] = K
+                p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
+        if pl["kind"] == PLATE_GENERIC:
+            saved, self.prog.code = self.prog.code, []
+            self.emit_expr(body)
+            self.prog.emit("END")
+            pl["body_prog"] = len(self._tail)
+            self._tail.extend(self.prog.code)
+            self.prog.code = saved
+            p.summary.append(f"plate GENERIC n={n} body={body.op}")
+        p.plates.append(pl)
+        return len(p.plates) - 1
+
+    def _grouped(self, mean: Sym, n: int):
+        """mu[g_i] with points sorted by group and groups covering a contiguous component range."""
+        col, off, stride, base, _pid = mean.val
+        if stride != 1: return None
+        g = self.t.columns[col][off: off + n]
+        gi = g.astype(np.int64)
+        if np.any(gi != g) or np.any(np.diff(gi) < 0): return None
+        lo, hi = int(gi[0]), int(gi[-1])
+        J = hi - lo + 1
+        start = np.searchsorted(gi, np.arange(lo, hi + 2), side="left").astype(np.float64)
+        return base + lo, J, self.t.add_column(start)
+
+    def _loglinear(self, eta: Sym):
+        """eta = sum_k X[i][k] * beta[k] (k ascending, optional leading 0), X row-major with row stride K."""
+        terms = _spine_terms(eta)
+        xcol = None
+        base = None
+        for k, tm in enumerate(terms):
+            if tm.op != "MUL": return None
+            a, b = tm.args
+            if a.op == "COMP" and b.op == "DATA_I": a, b = b, a
+            if not (a.op == "DATA_I" and b.op == "COMP"): return None
+            c, off, stride, _pid = a.val
+            if xcol is None: xcol, base = c, b.val
+            if c != xcol or off != k or stride != len(terms) or b.val != base + k: return None
+        if xcol is None or len(terms) > 16: return None
+        return xcol, len(terms), base
+
+    # -- main -------------------------------------------------------------------------------------
+    def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
+        p = self.prog
+        self._tail: List[int] = []
+        terms = _spine_terms(result)
+        i = 0
+        n_terms = len(terms)
+        while i < n_terms:
+            tm = terms[i]
+            pid = _has_plate_ref(tm)
+            if pid is not None:                                   # symbolic-index term: a plate as written
+                q = self._make_plate(tm, self.t.plate_sizes[pid])
+                p.emit("PLATE", q)
+                i += 1
+                continue
+            run = self._find_run(terms, i)
+            if run is not None:
+                body, length = run
+                q = self._make_plate(body, length)
+                p.emit("PLATE", q)
+                i += length
+                continue
+            self.emit_expr(tm)
+            p.emit("ACC")
+            p.summary.append(f"term {tm.op}")
+            i += 1
+        p.emit("END")
+        # derived quantities
+        if derived:
+            p.derived_prog = len(p.code)
+            for d, (name, expr) in enumerate(derived.items()):
+                self.emit_expr(lift(expr))
+                p.emit("STORE", d)
+                p.derived_names.append(name)
+            p.emit("END")
+        # operand programs live after the main programs
+        tail0 = len(p.code)
+        p.code.extend(self._tail)
+        for pl in p.plates:
+            pl["arg_prog"] = [a + tail0 if a >= 0 else -1 for a in pl["arg_prog"]]
+            if pl["body_prog"] >= 0: pl["body_prog"] += tail0
+        p.logpost_prog = 0
+        return p
+
+    def _find_run(self, terms: List[Sym], i0: int):
+        """Longest run starting at i0 of terms equal up to data positions that advance affinely. -> (body, length)."""
+        slots0: list = []
+        sig0 = _signature(terms[i0], slots0)
+        loose = False
+        if not slots0:
+            return None
+        # cheap pre-check with the next term
+        if i0 + 1 >= len(terms):
+            return None
+        s1: list = []
+        if _signature(terms[i0 + 1], s1) != sig0:
+            slots0 = []
+            sig0 = _signature_loose(terms[i0], slots0)
+            s1 = []
+            if _signature_loose(terms[i0 + 1], s1) != sig0:
+                return None
+            loose = True
+        sigf = _signature_loose if loose else _signature
+        seqs = [[s[2]] for s in slots0]
+        j = i0 + 1
+        while j < len(terms):
+            sl: list = []
+            if sigf(terms[j], sl) != sig0 or len(sl) != len(slots0):
+                break
+            if any(a[:2] != b[:2] for a, b in zip(sl, slots0)):
+                break
+            for k, s in enumerate(sl): seqs[k].append(s[2])
+            j += 1
+        length = j - i0
+        if length < _MIN_PLATE:
+            return None
+        # every data slot must advance affinely; component slots may be arbitrary (-> synthesized index column)
+        plan = []
+        for (kind, col, first), seq in zip(slots0, seqs):
+            arr = np.asarray(seq, dtype=np.int64)
+            if kind == "D":
+                stride = int(arr[1] - arr[0])
+                if np.any(np.diff(arr) != stride):
+                    # truncate the run at the first break
+                    brk = int(np.argmax(np.diff(arr) != stride)) + 1
+                    length = min(length, brk)
+                plan.append(("D", col, int(arr[0]), stride))
+            else:
+                plan.append(("C", arr))
+        if length < _MIN_PLATE:
+            return None
+        pid = self.t._n_plate_idx
+        self.t._n_plate_idx += 1
+        self.t.plate_sizes[pid] = length
+        final_plan = []
+        for item in plan:
+            if item[0] == "D":
+                final_plan.append(("DATA_I", (item[1], item[2], item[3], pid)))
+            else:
+                arr = item[1][:length]
+                if np.all(arr == arr[0]):
+                    final_plan.append(("COMP", int(arr[0])))
+                else:
+                    base = int(arr.min())
+                    col = self.t.add_column((arr - base).astype(np.float64))
+                    final_plan.append(("COMP_I", (col, 0, 1, base, pid)))
+        it = iter(final_plan)
+        body = self._rebuild(terms[i0], it, loose)
+        return body, length
+
+    def _rebuild(self, node: Sym, it, loose: bool) -> Sym:
+        if node.op == "DATA":
+            op, val = next(it)
+            return Sym(op, (), val)
+        if node.op == "COMP" and loose:
+            op, val = next(it)
+            return Sym(op, (), val)
+        if not node.args:
+            return node
+        return Sym(node.op, tuple(self._rebuild(a, it, loose) for a in node.args), node.val)
+
+
+def _lfactorial_host(y: float) -> float:
+    """lfactorial(y) = Lanczos lgamma(y+1), distributions.js:63-82. Only used to PRECOMPUTE a data column for
+    the Poisson plate (constant in the parameters). Plain fp64 ops in the JS order; math.log is within 1 ulp of
+    the device log, which moves the constant offset of log_post by < 1e-15 relative (it cancels in every accept ratio)."""
+    if y < 0: return float("nan")
+    x = y + 1.0
+    cof = [76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5]
+    ser = 1.000000000190015
+    xx = yy = x
+    tmp = x + 5.5
+    tmp -= (xx + 0.5) * math.log(tmp)
+    for c in cof:
+        yy += 1.0
+        ser += c / yy
+    return math.log(2.5066282746310005 * ser / xx) - tmp
+
+
+def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: int, data) -> Tuple[Program, List[str]]:
+    """Run `log_post` once symbolically; return the lowered program and the derived-quantity names."""
+    tr = Tracer()
+    state = tr.make_state(params, offsets)
+    wrapped = tr.wrap_data(data)
+    _ACTIVE.append(tr)
+    try:
+        result = log_post(state, wrapped)
+    finally:
+        _ACTIVE.pop()
+    if result is None:
+        raise JsThrow("log_post returned undefined")
+    result = lift(result)
+    derived = {k: v for k, v in state.items() if k not in params}
+    for k, v in derived.items():
+        if not isinstance(v, (Sym, numbers.Real)):
+            raise JsThrow(f"derived quantity {k} must be a number")
+    prog = Lowering(tr, n_comp).lower(result, derived)
+    return prog, list(derived.keys())
+
+
+_ACTIVE: List[Tracer] = []
+
+
+def points(n):
+    """``for i in mcmc.points(n):`` -- a loop over n data points recorded once (see PlateIndex)."""
+    if not _ACTIVE:
+        return range(int(n))
+    return _ACTIVE[-1].points(n)

@@ -1,0 +1,181 @@
+/*
+ * amwg.h -- C ABI of the B200-native many-chain AMWG sampler (libamwg_b200.so).
+ *
+ * The reference (rasmusab/bayes.js) has no FFI: its boundary is the JavaScript object API
+ *     new mcmc.AmwgSampler(params, log_post, data, options)   mcmc.js:1090-1092, 940-966
+ *     .burn(n) .sample(n) .step() .thin(k) .monitor(names)     mcmc.js:985-1055
+ *     .start_adaptation() .stop_adaptation() .info()           mcmc.js:1060-1073, 977-980
+ * This header is what a Node N-API addon (js/amwg_napi.cc) or any other host
+ * binds instead.  Plain pointers and sizes only; every call returns 0 or a negative status and
+ * amwg_last_error() gives the message the JS shim re-throws as a bare string (the reference
+ * throws strings, mcmc.js:165,299,315,340,445,490,495,636,746,790,867,972).
+ *
+ * Calls block until the result is usable; a handle is not thread-safe (the reference is
+ * single-threaded); all per-chain state stays resident in HBM between calls, so successive
+ * burn()/sample() calls continue the same chains (mcmc.js:964-965, 509-511).
+ *
+ * A handle owns `n_chains` independent chains with global ids [first_chain, first_chain+n_chains).
+ * Chain g behaves exactly like one run of the reference with Math.random() replaced by the
+ * Philox4x32-10 stream (seed, g) defined in DESIGN.md "RNG contract"; results therefore do not
+ * depend on how chains are sharded over handles / GPUs.
+ */
+#ifndef AMWG_H_
+#define AMWG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AMWG_ABI_VERSION 1
+
+/* ---- parameters: one entry per key of the completed `params` object (mcmc.js:357-403) ---- */
+enum { AMWG_REAL = 0, AMWG_INT = 1, AMWG_BINARY = 2 };
+
+typedef struct {
+  int32_t type;          /* AMWG_REAL | AMWG_INT | AMWG_BINARY                      (mcmc.js:844-868) */
+  int32_t n_comp;        /* prod(dim): scalar components, flattened row-major                          */
+  int32_t dim0;          /* dim[0]: the level visited in random order each sweep   (mcmc.js:244-263)  */
+  int32_t comp_offset;   /* index of the first component in the flat state vector                     */
+  double lower, upper;   /* bounds, +-inf allowed                                  (mcmc.js:497-498)  */
+} amwg_param;
+
+/* per scalar component: the options OnedimMetropolisStepper resolves (mcmc.js:500-505, 658-660) */
+typedef struct {
+  double prop_log_scale;       /* default 0    */
+  double batch_size;           /* default 50   */
+  double max_adaptation;       /* default 0.33 */
+  double initial_adaptation;   /* default 1.0  */
+  double target_accept_rate;   /* default 0.44 */
+  int32_t is_adapting;         /* default 1    */
+  int32_t _pad;
+} amwg_comp_options;
+
+/* ---- data: named fp64 columns (JS numbers); copied to the device at create ---- */
+typedef struct {
+  const double* values;
+  int64_t n;
+} amwg_column;
+
+/* ---- log_post as a program --------------------------------------------------------------
+ * log_post(state, data) (mcmc.js:958-960) arrives as a postfix program over an fp64 stack, one
+ * int32 word per instruction: (operand << 8) | opcode, plus one extra word where noted.
+ * The accumulator `lp` starts at 0 and receives terms strictly in program order, so the sum is
+ * formed in the same order as the JS `log_post += ...` statements.
+ * Every arithmetic op is a single IEEE-754 fp64 operation (no FMA contraction); LOG/EXP are the
+ * fdlibm algorithms V8's Math.log/Math.exp port; LD_* follow distributions.js operation by
+ * operation (cited per opcode in csrc/amwg_ld.cuh).
+ */
+enum {
+  AMWG_OP_END = 0,
+  AMWG_OP_CONST,        /* push consts[operand]                                             */
+  AMWG_OP_COMP,         /* push state component `operand` (proposal value for the moved one) */
+  AMWG_OP_DATA,         /* push columns[operand][next word]                                  */
+  AMWG_OP_DATA_I,       /* push columns[operand][off + stride*i], i = plate point; next words: off, stride */
+  AMWG_OP_COMP_I,       /* push state component base + (int)columns[operand][off + stride*i]; next words: off, stride, base */
+  AMWG_OP_ADD, AMWG_OP_SUB, AMWG_OP_MUL, AMWG_OP_DIV, AMWG_OP_NEG,
+  AMWG_OP_LOG, AMWG_OP_EXP, AMWG_OP_SQRT, AMWG_OP_ABS, AMWG_OP_POW,
+  AMWG_OP_LT, AMWG_OP_LE, AMWG_OP_GT, AMWG_OP_GE, AMWG_OP_EQ, AMWG_OP_NE,   /* push 1.0 / 0.0 */
+  AMWG_OP_AND, AMWG_OP_OR, AMWG_OP_NOT,
+  AMWG_OP_SELECT,       /* pops b, a, c ; pushes c != 0 ? a : b                              */
+  AMWG_OP_LGAMMA, AMWG_OP_LFACTORIAL, AMWG_OP_LCHOOSE, AMWG_OP_LBETA,   /* distributions.js:63-92 */
+  AMWG_OP_LD_NORM, AMWG_OP_LD_UNIF, AMWG_OP_LD_BETA, AMWG_OP_LD_BERN, AMWG_OP_LD_POIS,
+  AMWG_OP_LD_CAUCHY, AMWG_OP_LD_LAPLACE, AMWG_OP_LD_GAMMA, AMWG_OP_LD_INVGAMMA, AMWG_OP_LD_LNORM,
+  AMWG_OP_LD_PARETO, AMWG_OP_LD_T, AMWG_OP_LD_WEIBULL, AMWG_OP_LD_LOGIS, AMWG_OP_LD_EXP,
+  AMWG_OP_LD_BINOM, AMWG_OP_LD_NBINOM, AMWG_OP_LD_HYPER,
+  AMWG_OP_ACC,          /* lp = lp + pop                                                     */
+  AMWG_OP_PLATE,        /* lp = plate[operand](lp)  : the O(N) likelihood sum                */
+  AMWG_OP_STORE,        /* derived[operand] = pop   (derived-quantity program only)          */
+  AMWG_OP__COUNT
+};
+
+/* A plate is a run of N structurally identical likelihood terms, `for (i...) log_post += ld.X(data[i], ...)`.
+ * Recognised shapes get a hand-written inner loop; anything else runs its body program per point. */
+enum {
+  AMWG_PLATE_GENERIC = 0,   /* body program evaluated per point, lp += body(i) in order (bit-faithful)          */
+  AMWG_PLATE_NORM_IID,      /* sum_i ld.norm(x_i, mean, sd); mean, sd index-free.  Factorised:
+                               N*(-0.5*log(2pi) - log(sd)) - sum_i (x_i-mean)^2 / (2*sd*sd)   (KS-level parity) */
+  AMWG_PLATE_BERN_IID,      /* sum_i ld.bern(y_i, p); p index-free; sequential, bit-faithful                     */
+  AMWG_PLATE_NORM_GROUPED,  /* sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group                            */
+  AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k))                                        */
+};
+
+typedef struct {
+  int32_t kind;          /* AMWG_PLATE_*                                                          */
+  int32_t n;             /* number of points                                                       */
+  int32_t col[4];        /* data columns: [0] x or y; GROUPED: [1] group start offsets (J+1);
+                            POIS_LOGLIN: [1] X row-major n*K, [2] lfactorial(y) (filled by the host) */
+  int32_t arg_prog[4];   /* word offsets of index-free operand programs (END-terminated), -1 unused:
+                            NORM_*: [0] mean (IID only), [1] sd;  BERN: [0] p                        */
+  int32_t iparam[4];     /* GROUPED: [0] first mu component, [1] J;  POIS_LOGLIN: [0] first beta component, [1] K;
+                            all specialised kinds: [2] offset of the plate's first point inside col[0]              */
+  int32_t body_prog;     /* GENERIC: word offset of the per-point program (uses DATA_I / COMP_I)     */
+  int32_t _pad;
+} amwg_plate;
+
+typedef struct {
+  int32_t abi_version;                     /* AMWG_ABI_VERSION */
+  int32_t n_params;   const amwg_param* params;
+  int32_t n_comp;     const double* init;                  /* params[*].init flattened, length n_comp */
+  const amwg_comp_options* comp_options;                   /* length n_comp (ignored for binary)      */
+  int32_t n_code;     const int32_t* code;                 /* all programs, concatenated              */
+  int32_t logpost_prog;                                    /* word offset of the log_post program     */
+  int32_t derived_prog;                                    /* word offset of the derived program, -1  */
+  int32_t n_derived;                                       /* derived quantities (state keys beyond params, mcmc.js:990) */
+  int32_t n_consts;   const double* consts;
+  int32_t n_columns;  const amwg_column* columns;
+  int32_t n_plates;   const amwg_plate* plates;
+} amwg_model;
+
+typedef struct amwg_sampler amwg_sampler;
+
+/* new mcmc.AmwgSampler(...) for n_chains chains on CUDA device `device` (mcmc.js:1090-1092, 940-966):
+ * uploads the model, places every chain at params[*].init and evaluates log_post once. */
+int amwg_create(const amwg_model* model, uint64_t n_chains, uint64_t first_chain, uint64_t seed,
+                int device, amwg_sampler** out);
+void amwg_destroy(amwg_sampler* s);
+
+/* sampler.burn(n) -- mcmc.js:1035-1039 */
+int amwg_burn(amwg_sampler* s, int64_t n);
+
+/* sampler.sample(n) with thinning interval `thin` and the monitored entries `monitor[n_monitor]`
+ * (index < n_comp: state component; n_comp + d: derived quantity d) -- mcmc.js:1005-1030.
+ * Row r is the state BEFORE sweep r*thin (row 0 is the pre-existing state, mcmc.js:1021-1027).
+ * Output layout: out[row][monitor][chain], fp64, rows = ceil(n/thin).
+ *   amwg_sample        : host buffer (pinned memory recommended); D2H copies overlap the sweeps.
+ *   amwg_sample_device : device buffer on the handle's device; no host traffic. */
+int amwg_sample(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* host_out);
+int amwg_sample_device(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* dev_out);
+
+/* live state, as sampler.step() returns it (mcmc.js:985-997): out[entry][chain], entries = n_comp + n_derived */
+int amwg_get_state(amwg_sampler* s, double* host_out);
+
+/* sampler.start_adaptation() / stop_adaptation() -- mcmc.js:1060-1073 */
+int amwg_set_adapting(amwg_sampler* s, int32_t flag);
+
+/* stepper info() (mcmc.js:563-571): per component, chain-invariant counters and per-chain arrays.
+ * scalars[c*3 + {0,1,2}] = is_adapting, iterations_since_adaption, batch_count  (host, length 3*n_comp)
+ * prop_log_scale[c][chain], acceptance_count[c][chain] (host; either may be NULL) */
+int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scale, int32_t* acceptance_count);
+
+/* instrumentation */
+int64_t amwg_kernel_launches(const amwg_sampler* s);   /* kernels this handle has launched so far       */
+double amwg_last_sweep_kernel_ms(const amwg_sampler* s); /* CUDA-event time of the sweep kernels of the last burn/sample call */
+uint64_t amwg_n_chains(const amwg_sampler* s);
+
+const char* amwg_last_error(void);
+int amwg_abi_version(void);
+
+/* ld.* evaluated on the device, one value per input row (used by the `ld` host module and by the
+ * parity tests): op is an AMWG_OP_LD_* / AMWG_OP_LGAMMA.. opcode, args is [n][arity] row-major. */
+int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device);
+
+/* Math.log / Math.exp / the Philox uniform stream on the device, for parity tests of the primitives.
+ * kind: 0 log, 1 exp, 2 stream uniform (x[i] reinterpreted: out[i] = uniform #i of chain `chain`), 3 rnorm(0,1) draw i.. */
+int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AMWG_H_ */
