@@ -532,16 +532,39 @@ class AmwgSampler(Sampler):
         return list(self._program.summary)
 
 
+class _PinnedPool:
+    """Page-locked host buffers for sample(): pinning GBs costs more than the copy itself, so buffers are recycled once
+    every array handed to the user (all views of the buffer) has been garbage collected."""
+
+    def __init__(self):
+        self._free: Dict[tuple, list] = {}
+
+    def get(self, shape) -> np.ndarray:
+        shape = tuple(int(v) for v in shape)
+        try:
+            import torch
+            if not torch.cuda.is_available():
+                raise RuntimeError
+        except Exception:
+            return np.empty(shape, dtype=np.float64)
+        import weakref
+        lst = self._free.get(shape)
+        t = lst.pop() if lst else torch.empty(shape, dtype=torch.float64, pin_memory=True)
+        a = t.numpy()
+        weakref.finalize(a, self._put, shape, t)
+        return a
+
+    def _put(self, shape, t):
+        lst = self._free.setdefault(shape, [])
+        if len(lst) < 2:
+            lst.append(t)
+
+
+_PINNED = _PinnedPool()
+
+
 def _pinned_empty(shape) -> np.ndarray:
-    """Host buffer for sample(): page-locked through torch when a GPU is present (the D2H copies then overlap the
-    sweeps), else pageable. The numpy view keeps the tensor alive."""
-    try:
-        import torch
-        if torch.cuda.is_available():
-            return torch.empty(tuple(int(v) for v in shape), dtype=torch.float64, pin_memory=True).numpy()
-    except Exception:
-        pass
-    return np.empty(shape, dtype=np.float64)
+    return _PINNED.get(shape)
 
 
 def _not_on_device(name):

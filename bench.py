@@ -164,7 +164,7 @@ def run_ours(args):
     sampler = mcmc.AmwgSampler(PARAMS, make_log_post(ld), config2_data().tolist(),
                                {"chains": chains_total, "seed": 0, "device": local_rank, "distributed": world > 1})
     local = sampler.local_chains
-    sampler.burn(BURN)
+    sampler.burn(args.burn)
     mon = np.array([0, 1], dtype=np.int32)
     monp = mon.ctypes.data_as(C.POINTER(C.c_int32))
     dev_out = torch.empty((iters, 2, local), dtype=torch.float64, device=f"cuda:{local_rank}")
@@ -225,7 +225,7 @@ def run_ours(args):
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "config 2: Normal(mu,sigma), N=1024 synthetic, 2^20 chains per GPU", "chains_per_gpu": local,
-                       "chains_total": chains_total, "iters_per_step": iters, "burn_in_setup": BURN, "adapting": True,
+                       "chains_total": chains_total, "iters_per_step": iters, "burn_in_setup": args.burn, "adapting": True,
                        "parallelism": f"chains sharded x{world}, no data-path collective",
                        "l2": "every step writes its samples (iters*2*chains*8 B = %.2f GB > 126 MB L2), which flushes L2" % (iters * 2 * local * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
@@ -259,6 +259,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--chains", type=int, default=CHAINS_PER_GPU, help="chains per GPU")
     ap.add_argument("--iters", type=int, default=ITERS, help="sweeps per step")
+    ap.add_argument("--burn", type=int, default=BURN, help="burn-in sweeps done in setup (untimed)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -29,6 +29,11 @@ extern "C" {
 #endif
 
 #define AMWG_ABI_VERSION 1
+#if defined(__GNUC__)
+#define AMWG_API __attribute__((visibility("default")))
+#else
+#define AMWG_API
+#endif
 
 /* ---- parameters: one entry per key of the completed `params` object (mcmc.js:357-403) ---- */
 enum { AMWG_REAL = 0, AMWG_INT = 1, AMWG_BINARY = 2 };
@@ -132,12 +137,12 @@ typedef struct amwg_sampler amwg_sampler;
 
 /* new mcmc.AmwgSampler(...) for n_chains chains on CUDA device `device` (mcmc.js:1090-1092, 940-966):
  * uploads the model, places every chain at params[*].init and evaluates log_post once. */
-int amwg_create(const amwg_model* model, uint64_t n_chains, uint64_t first_chain, uint64_t seed,
+AMWG_API int amwg_create(const amwg_model* model, uint64_t n_chains, uint64_t first_chain, uint64_t seed,
                 int device, amwg_sampler** out);
-void amwg_destroy(amwg_sampler* s);
+AMWG_API void amwg_destroy(amwg_sampler* s);
 
 /* sampler.burn(n) -- mcmc.js:1035-1039 */
-int amwg_burn(amwg_sampler* s, int64_t n);
+AMWG_API int amwg_burn(amwg_sampler* s, int64_t n);
 
 /* sampler.sample(n) with thinning interval `thin` and the monitored entries `monitor[n_monitor]`
  * (index < n_comp: state component; n_comp + d: derived quantity d) -- mcmc.js:1005-1030.
@@ -145,35 +150,35 @@ int amwg_burn(amwg_sampler* s, int64_t n);
  * Output layout: out[row][monitor][chain], fp64, rows = ceil(n/thin).
  *   amwg_sample        : host buffer (pinned memory recommended); D2H copies overlap the sweeps.
  *   amwg_sample_device : device buffer on the handle's device; no host traffic. */
-int amwg_sample(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* host_out);
-int amwg_sample_device(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* dev_out);
+AMWG_API int amwg_sample(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* host_out);
+AMWG_API int amwg_sample_device(amwg_sampler* s, int64_t n, int64_t thin, const int32_t* monitor, int32_t n_monitor, double* dev_out);
 
 /* live state, as sampler.step() returns it (mcmc.js:985-997): out[entry][chain], entries = n_comp + n_derived */
-int amwg_get_state(amwg_sampler* s, double* host_out);
+AMWG_API int amwg_get_state(amwg_sampler* s, double* host_out);
 
 /* sampler.start_adaptation() / stop_adaptation() -- mcmc.js:1060-1073 */
-int amwg_set_adapting(amwg_sampler* s, int32_t flag);
+AMWG_API int amwg_set_adapting(amwg_sampler* s, int32_t flag);
 
 /* stepper info() (mcmc.js:563-571): per component, chain-invariant counters and per-chain arrays.
  * scalars[c*3 + {0,1,2}] = is_adapting, iterations_since_adaption, batch_count  (host, length 3*n_comp)
  * prop_log_scale[c][chain], acceptance_count[c][chain] (host; either may be NULL) */
-int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scale, int32_t* acceptance_count);
+AMWG_API int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scale, int32_t* acceptance_count);
 
 /* instrumentation */
-int64_t amwg_kernel_launches(const amwg_sampler* s);   /* kernels this handle has launched so far       */
-double amwg_last_sweep_kernel_ms(const amwg_sampler* s); /* CUDA-event time of the sweep kernels of the last burn/sample call */
-uint64_t amwg_n_chains(const amwg_sampler* s);
+AMWG_API int64_t amwg_kernel_launches(const amwg_sampler* s);   /* kernels this handle has launched so far       */
+AMWG_API double amwg_last_sweep_kernel_ms(const amwg_sampler* s); /* CUDA-event time of the sweep kernels of the last burn/sample call */
+AMWG_API uint64_t amwg_n_chains(const amwg_sampler* s);
 
-const char* amwg_last_error(void);
-int amwg_abi_version(void);
+AMWG_API const char* amwg_last_error(void);
+AMWG_API int amwg_abi_version(void);
 
 /* ld.* evaluated on the device, one value per input row (used by the `ld` host module and by the
  * parity tests): op is an AMWG_OP_LD_* / AMWG_OP_LGAMMA.. opcode, args is [n][arity] row-major. */
-int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device);
+AMWG_API int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device);
 
 /* Math.log / Math.exp / the Philox uniform stream on the device, for parity tests of the primitives.
  * kind: 0 log, 1 exp, 2 stream uniform (x[i] reinterpreted: out[i] = uniform #i of chain `chain`), 3 rnorm(0,1) draw i.. */
-int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device);
+AMWG_API int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device);
 
 #ifdef __cplusplus
 }
