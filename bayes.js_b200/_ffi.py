@@ -15,12 +15,12 @@ LIB_PATH = os.path.join(_HERE, "libamwg_b200.so")
 # ---- opcodes / plate kinds: keep in sync with include/amwg.h (checked by tests/test_abi.py) ----
 _OPS = """END CONST COMP DATA DATA_I COMP_I ADD SUB MUL DIV NEG LOG EXP SQRT ABS POW LT LE GT GE EQ NE AND OR NOT SELECT
 LGAMMA LFACTORIAL LCHOOSE LBETA LD_NORM LD_UNIF LD_BETA LD_BERN LD_POIS LD_CAUCHY LD_LAPLACE LD_GAMMA LD_INVGAMMA
-LD_LNORM LD_PARETO LD_T LD_WEIBULL LD_LOGIS LD_EXP LD_BINOM LD_NBINOM LD_HYPER ACC PLATE STORE""".split()
+LD_LNORM LD_PARETO LD_T LD_WEIBULL LD_LOGIS LD_EXP LD_BINOM LD_NBINOM LD_HYPER ACC PLATE STORE LOOP_BEGIN LOOP_END""".split()
 OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)
 REAL, INT, BINARY = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class AmwgParam(C.Structure):
@@ -39,8 +39,7 @@ class AmwgColumn(C.Structure):
 
 
 class AmwgPlate(C.Structure):
-    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("col", C.c_int32 * 4), ("arg_prog", C.c_int32 * 4),
-                ("iparam", C.c_int32 * 4), ("body_prog", C.c_int32), ("_pad", C.c_int32)]
+    _fields_ = [("kind", C.c_int32), ("n", C.c_int32), ("col", C.c_int32 * 4), ("iparam", C.c_int32 * 4)]
 
 
 class AmwgModel(C.Structure):
@@ -52,7 +51,8 @@ class AmwgModel(C.Structure):
                 ("logpost_prog", C.c_int32), ("derived_prog", C.c_int32), ("n_derived", C.c_int32),
                 ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double)),
                 ("n_columns", C.c_int32), ("columns", C.POINTER(AmwgColumn)),
-                ("n_plates", C.c_int32), ("plates", C.POINTER(AmwgPlate))]
+                ("n_plates", C.c_int32), ("plates", C.POINTER(AmwgPlate)),
+                ("n_fold", C.c_int32), ("fold_prog", C.POINTER(C.c_int32)), ("fold_dst", C.POINTER(C.c_int32))]
 
 
 EXPORTS = ["amwg_create", "amwg_destroy", "amwg_burn", "amwg_sample", "amwg_sample_device", "amwg_get_state",

@@ -55,6 +55,7 @@ struct ModelDev {
 struct ChainArrays {
   double* state;          // [D][C]
   double* pls;            // [D][C] prop_log_scale
+  double* psd;            // [D][C] exp(prop_log_scale): the proposal sd, recomputed only when pls changes (same bits as mcmc.js:578)
   int* acc;               // [D][C] acceptance_count of the current batch
   double* curr_lp;        // [C]   cached log_post(state)
   unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
@@ -79,7 +80,8 @@ struct Ctx {                       // lives in shared memory
   const double* consts;
   const amwg_plate* plates;
   const amwg_param* params;
-  const double* col[kMaxColumns];
+  const double* col[kMaxColumns];  // generic pointers (shared or global)
+  unsigned col_saddr[kMaxColumns]; // 32-bit shared-window address, 0 when the column is served from global/L2
 };
 
 struct EvalState {
@@ -110,6 +112,11 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gme
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+__device__ __forceinline__ double2 lds_f64x2(unsigned saddr) {
+  double2 v;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+  return v;
+}
 
 // Stage the model image and every data column that fits into shared memory; fill ctx. All threads call this.
 __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* smem, Ctx& ctx, unsigned long long* bar) {
@@ -130,113 +137,59 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
     ctx.consts = reinterpret_cast<const double*>(smem + m.off_consts);
     ctx.plates = reinterpret_cast<const amwg_plate*>(smem + m.off_plates);
     ctx.params = reinterpret_cast<const amwg_param*>(smem + m.off_params);
-    for (int k = 0; k < m.n_columns; ++k)
-      ctx.col[k] = m.col_smem_off[k] >= 0 ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
+    for (int k = 0; k < m.n_columns; ++k) {
+      bool in_smem = m.col_smem_off[k] >= 0;
+      ctx.col[k] = in_smem ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
+      ctx.col_saddr[k] = in_smem ? smem_u32(smem + m.col_smem_off[k]) : 0u;
+    }
   }
   __syncthreads();
   mbar_wait(bar, 0);
 }
 
-// ---- expression interpreter -----------------------------------------------------------------------------------
-// Executes one non-accumulating instruction on the stack. Returns false for END/ACC/PLATE/STORE (caller handles).
-__device__ __forceinline__ bool exec_basic(const Ctx& ctx, const EvalState& es, int op, int a, int& pc, double* stk, int& sp, int plate_i) {
-  switch (op) {
-    case AMWG_OP_CONST: stk[sp++] = ctx.consts[a]; return true;
-    case AMWG_OP_COMP: stk[sp++] = es.comp(a); return true;
-    case AMWG_OP_DATA: stk[sp++] = ctx.col[a][ctx.code[pc++]]; return true;
-    case AMWG_OP_DATA_I: { int off = ctx.code[pc++], stride = ctx.code[pc++]; stk[sp++] = ctx.col[a][off + stride * plate_i]; return true; }
-    case AMWG_OP_COMP_I: {
-      int off = ctx.code[pc++], stride = ctx.code[pc++], base = ctx.code[pc++];
-      stk[sp++] = es.comp(base + (int)ctx.col[a][off + stride * plate_i]);
-      return true;
-    }
-    case AMWG_OP_ADD: sp--; stk[sp - 1] = stk[sp - 1] + stk[sp]; return true;
-    case AMWG_OP_SUB: sp--; stk[sp - 1] = stk[sp - 1] - stk[sp]; return true;
-    case AMWG_OP_MUL: sp--; stk[sp - 1] = stk[sp - 1] * stk[sp]; return true;
-    case AMWG_OP_DIV: sp--; stk[sp - 1] = stk[sp - 1] / stk[sp]; return true;
-    case AMWG_OP_NEG: stk[sp - 1] = -stk[sp - 1]; return true;
-    case AMWG_OP_LOG: stk[sp - 1] = js_log(stk[sp - 1]); return true;
-    case AMWG_OP_EXP: stk[sp - 1] = js_exp(stk[sp - 1]); return true;
-    case AMWG_OP_SQRT: stk[sp - 1] = sqrt(stk[sp - 1]); return true;
-    case AMWG_OP_ABS: stk[sp - 1] = fabs(stk[sp - 1]); return true;
-    case AMWG_OP_POW: sp--; stk[sp - 1] = js_pow(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LT: sp--; stk[sp - 1] = stk[sp - 1] < stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_LE: sp--; stk[sp - 1] = stk[sp - 1] <= stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_GT: sp--; stk[sp - 1] = stk[sp - 1] > stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_GE: sp--; stk[sp - 1] = stk[sp - 1] >= stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_EQ: sp--; stk[sp - 1] = stk[sp - 1] == stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_NE: sp--; stk[sp - 1] = stk[sp - 1] != stk[sp] ? 1.0 : 0.0; return true;
-    case AMWG_OP_AND: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 && stk[sp] != 0.0) ? 1.0 : 0.0; return true;
-    case AMWG_OP_OR: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 || stk[sp] != 0.0) ? 1.0 : 0.0; return true;
-    case AMWG_OP_NOT: stk[sp - 1] = stk[sp - 1] != 0.0 ? 0.0 : 1.0; return true;
-    case AMWG_OP_SELECT: sp -= 2; stk[sp - 1] = stk[sp - 1] != 0.0 ? stk[sp] : stk[sp + 1]; return true;
-    case AMWG_OP_LGAMMA: stk[sp - 1] = ld_lgamma(stk[sp - 1]); return true;
-    case AMWG_OP_LFACTORIAL: stk[sp - 1] = ld_lfactorial(stk[sp - 1]); return true;
-    case AMWG_OP_LCHOOSE: sp--; stk[sp - 1] = ld_lchoose(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LBETA: sp--; stk[sp - 1] = ld_lbeta(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LD_NORM: sp -= 2; stk[sp - 1] = ld_norm(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_UNIF: sp -= 2; stk[sp - 1] = ld_unif(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_BETA: sp -= 2; stk[sp - 1] = ld_beta(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_BERN: sp--; stk[sp - 1] = ld_bern(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LD_POIS: sp--; stk[sp - 1] = ld_pois(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LD_CAUCHY: sp -= 2; stk[sp - 1] = ld_cauchy(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_LAPLACE: sp -= 2; stk[sp - 1] = ld_laplace(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_GAMMA: sp -= 2; stk[sp - 1] = ld_gamma(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_INVGAMMA: sp -= 2; stk[sp - 1] = ld_invgamma(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_LNORM: sp -= 2; stk[sp - 1] = ld_lnorm(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_PARETO: sp -= 2; stk[sp - 1] = ld_pareto(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_T: sp -= 3; stk[sp - 1] = ld_t(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); return true;
-    case AMWG_OP_LD_WEIBULL: sp -= 2; stk[sp - 1] = ld_weibull(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_LOGIS: sp -= 2; stk[sp - 1] = ld_logis(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_EXP: sp--; stk[sp - 1] = ld_exp(stk[sp - 1], stk[sp]); return true;
-    case AMWG_OP_LD_BINOM: sp -= 2; stk[sp - 1] = ld_binom(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_NBINOM: sp -= 2; stk[sp - 1] = ld_nbinom(stk[sp - 1], stk[sp], stk[sp + 1]); return true;
-    case AMWG_OP_LD_HYPER: sp -= 3; stk[sp - 1] = ld_hyper(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); return true;
-    default: return false;
-  }
-}
-
-// Evaluate an END-terminated expression program; returns the top of stack.
-__device__ __noinline__ double eval_expr(const Ctx& ctx, const EvalState& es, int pc, int plate_i) {
-  double stk[kStack];
-  int sp = 0;
-  for (;;) {
-    int w = ctx.code[pc++];
-    int op = w & 0xff, a = w >> 8;
-    if (!exec_basic(ctx, es, op, a, pc, stk, sp, plate_i)) break;
-  }
-  return sp > 0 ? stk[sp - 1] : 0.0;
-}
-
 // ---- plates: the O(N) likelihood sums -----------------------------------------------------------------------------
-// sum_i ld.norm(x_i, mean, sd), factorised (amwg.h AMWG_PLATE_NORM_IID). 2 fp64 pipe instructions per point
-// (DADD + DFMA), x_i read as 16-byte warp-broadcast shared-memory loads, 4 independent accumulators.
-__device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, int n, double mean) {
+// sum_i (x_i - mean)^2 : 2 fp64-pipe instructions per point (DADD + DFMA), 4 independent accumulators, x read as 16-byte
+// warp-broadcast loads.  `saddr` != 0: the column sits in shared memory (ld.shared.v2.f64, 32-bit addressing).
+__device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, unsigned saddr, int n, double mean) {
   double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
   int i = 0;
   if ((reinterpret_cast<unsigned long long>(x) & 15ull) && n > 0) { double d = x[0] - mean; s3 = fma(d, d, s3); i = 1; }   // 16B-align the vector loads
+  if (saddr) {
+    unsigned a = saddr + 8u * (unsigned)i;
 #pragma unroll 4
-  for (; i + 4 <= n; i += 4) {
-    double2 a = *reinterpret_cast<const double2*>(x + i);
-    double2 b = *reinterpret_cast<const double2*>(x + i + 2);
-    double d0 = a.x - mean, d1 = a.y - mean, d2 = b.x - mean, d3 = b.y - mean;
-    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+    for (; i + 4 <= n; i += 4, a += 32u) {
+      double2 p = lds_f64x2(a), q = lds_f64x2(a + 16u);
+      double d0 = p.x - mean, d1 = p.y - mean, d2 = q.x - mean, d3 = q.y - mean;
+      s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+    }
+  } else {
+#pragma unroll 4
+    for (; i + 4 <= n; i += 4) {
+      double2 p = *reinterpret_cast<const double2*>(x + i), q = *reinterpret_cast<const double2*>(x + i + 2);
+      double d0 = p.x - mean, d1 = p.y - mean, d2 = q.x - mean, d3 = q.y - mean;
+      s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);
+    }
   }
   for (; i < n; ++i) { double d = x[i] - mean; s0 = fma(d, d, s0); }
   return (s0 + s1) + (s2 + s3);
 }
 
-__device__ __forceinline__ double plate_norm_iid(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
-  double mean = eval_expr(ctx, es, pl.arg_prog[0], 0);
-  double sd = eval_expr(ctx, es, pl.arg_prog[1], 0);
-  double S = sum_sq_dev(ctx.col[pl.col[0]] + pl.iparam[2], pl.n, mean);
+__device__ __forceinline__ double norm_factorised(double n, double S, double sd) {
   double c0 = -0.5 * js_log(2 * AMWG_JS_PI);
-  return lp + ((double)pl.n * (c0 - js_log(sd)) - S / (2 * sd * sd));
+  return n * (c0 - js_log(sd)) - S / (2 * sd * sd);
+}
+
+__device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean, double sd) {
+  const amwg_plate& pl = ctx.plates[q];
+  int c = pl.col[0], off = pl.iparam[2];
+  unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)off : 0u;
+  double S = sum_sq_dev(ctx.col[c] + off, sa, pl.n, mean);
+  return norm_factorised((double)pl.n, S, sd);
 }
 
 // sum_i ld.bern(y_i, p): sequential, bit-faithful to distributions.js:228-230 (x*prob + (1-x)*(1-prob) is exact for x in {0,1}).
-__device__ __forceinline__ double plate_bern_iid(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
-  double p = eval_expr(ctx, es, pl.arg_prog[0], 0);
+__device__ __noinline__ double plate_bern_iid(const Ctx& ctx, int q, double p, double lp) {
+  const amwg_plate& pl = ctx.plates[q];
   double l1 = js_log(1.0 * p + (1 - 1.0) * (1 - p));
   double l0 = js_log(0.0 * p + (1 - 0.0) * (1 - p));
   const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
@@ -248,23 +201,24 @@ __device__ __forceinline__ double plate_bern_iid(const Ctx& ctx, const amwg_plat
 }
 
 // sum_i ld.norm(y_i, mu[g_i], sd) with points sorted by group; group j occupies [start[j], start[j+1]).
-__device__ __forceinline__ double plate_norm_grouped(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
-  double sd = eval_expr(ctx, es, pl.arg_prog[1], 0);
-  const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
+__device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const EvalState& es, double sd) {
+  const amwg_plate& pl = ctx.plates[q];
+  int c = pl.col[0], off = pl.iparam[2];
   const double* __restrict__ start = ctx.col[pl.col[1]];
   int J = pl.iparam[1], base = pl.iparam[0];
   double S = 0.0;
   for (int j = 0; j < J; ++j) {
-    int a = (int)start[j], b = (int)start[j + 1];
-    S = S + sum_sq_dev(y + a, b - a, es.comp(base + j));
+    int a = (int)start[j] + off, b = (int)start[j + 1] + off;
+    unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)a : 0u;
+    S = S + sum_sq_dev(ctx.col[c] + a, sa, b - a, es.comp(base + j));
   }
-  double c0 = -0.5 * js_log(2 * AMWG_JS_PI);
-  return lp + ((double)pl.n * (c0 - js_log(sd)) - S / (2 * sd * sd));
+  return norm_factorised((double)pl.n, S, sd);
 }
 
 // sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop), using log(exp(eta)) -> eta
 // and the precomputed lfactorial(y_i) column:  y*eta - exp(eta) - lfact.  (KS-level parity; real parameters only.)
-__device__ __forceinline__ double plate_pois_loglin(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
+__device__ __noinline__ double plate_pois_loglin(const Ctx& ctx, int q, const EvalState& es) {
+  const amwg_plate& pl = ctx.plates[q];
   const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
   const double* __restrict__ X = ctx.col[pl.col[1]];
   const double* __restrict__ lf = ctx.col[pl.col[2]];
@@ -278,54 +232,116 @@ __device__ __forceinline__ double plate_pois_loglin(const Ctx& ctx, const amwg_p
     double t = fma(y[i], eta, -exp(eta)) - lf[i];
     if (i & 1) s1 += t; else s0 += t;
   }
-  return lp + (s0 + s1);
+  return s0 + s1;
 }
 
-__device__ __forceinline__ double plate_generic(const Ctx& ctx, const amwg_plate& pl, const EvalState& es, double lp) {
-  for (int i = 0; i < pl.n; ++i) lp = lp + eval_expr(ctx, es, pl.body_prog, i);
-  return lp;
-}
-
-// log_post(state with component `moved` replaced by `val`): terms accumulate in program order.
-__device__ __noinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
+// ---- the interpreter: ONE instance of the opcode switch in the whole library ---------------------------------------------
+// Runs the program at `pc` to its END.  log_post programs accumulate into lp (ACC / PLATE / LOOP_END) and return it;
+// expression programs (constant folding) return the top of stack; derived programs STORE into der[].
+__device__ __noinline__ double run_program(const Ctx& ctx, const EvalState& es, int pc, double* der, bool want_top) {
   double stk[kStack];
   int sp = 0;
   double lp = 0.0;
+  int loop_i = 0, loop_n = 0;
   for (;;) {
-    int w = ctx.code[pc++];
-    int op = w & 0xff, a = w >> 8;
-    if (exec_basic(ctx, es, op, a, pc, stk, sp, 0)) continue;
-    if (op == AMWG_OP_ACC) { lp = lp + stk[--sp]; continue; }
-    if (op == AMWG_OP_PLATE) {
-      const amwg_plate& pl = ctx.plates[a];
-      switch (pl.kind) {
-        case AMWG_PLATE_NORM_IID: lp = plate_norm_iid(ctx, pl, es, lp); break;
-        case AMWG_PLATE_BERN_IID: lp = plate_bern_iid(ctx, pl, es, lp); break;
-        case AMWG_PLATE_NORM_GROUPED: lp = plate_norm_grouped(ctx, pl, es, lp); break;
-        case AMWG_PLATE_POIS_LOGLIN: lp = plate_pois_loglin(ctx, pl, es, lp); break;
-        default: lp = plate_generic(ctx, pl, es, lp); break;
+    const int w = ctx.code[pc++];
+    const int op = w & 0xff, a = w >> 8;
+    switch (op) {
+      case AMWG_OP_CONST: stk[sp++] = ctx.consts[a]; break;
+      case AMWG_OP_COMP: stk[sp++] = es.comp(a); break;
+      case AMWG_OP_DATA: stk[sp++] = ctx.col[a][ctx.code[pc++]]; break;
+      case AMWG_OP_DATA_I: { int off = ctx.code[pc++], stride = ctx.code[pc++]; stk[sp++] = ctx.col[a][off + stride * loop_i]; break; }
+      case AMWG_OP_COMP_I: {
+        int off = ctx.code[pc++], stride = ctx.code[pc++], base = ctx.code[pc++];
+        stk[sp++] = es.comp(base + (int)ctx.col[a][off + stride * loop_i]);
+        break;
       }
-      continue;
+      case AMWG_OP_ADD: sp--; stk[sp - 1] = stk[sp - 1] + stk[sp]; break;
+      case AMWG_OP_SUB: sp--; stk[sp - 1] = stk[sp - 1] - stk[sp]; break;
+      case AMWG_OP_MUL: sp--; stk[sp - 1] = stk[sp - 1] * stk[sp]; break;
+      case AMWG_OP_DIV: sp--; stk[sp - 1] = stk[sp - 1] / stk[sp]; break;
+      case AMWG_OP_NEG: stk[sp - 1] = -stk[sp - 1]; break;
+      case AMWG_OP_LOG: stk[sp - 1] = js_log(stk[sp - 1]); break;
+      case AMWG_OP_EXP: stk[sp - 1] = js_exp(stk[sp - 1]); break;
+      case AMWG_OP_SQRT: stk[sp - 1] = sqrt(stk[sp - 1]); break;
+      case AMWG_OP_ABS: stk[sp - 1] = fabs(stk[sp - 1]); break;
+      case AMWG_OP_POW: sp--; stk[sp - 1] = js_pow(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LT: sp--; stk[sp - 1] = stk[sp - 1] < stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_LE: sp--; stk[sp - 1] = stk[sp - 1] <= stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_GT: sp--; stk[sp - 1] = stk[sp - 1] > stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_GE: sp--; stk[sp - 1] = stk[sp - 1] >= stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_EQ: sp--; stk[sp - 1] = stk[sp - 1] == stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_NE: sp--; stk[sp - 1] = stk[sp - 1] != stk[sp] ? 1.0 : 0.0; break;
+      case AMWG_OP_AND: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 && stk[sp] != 0.0) ? 1.0 : 0.0; break;
+      case AMWG_OP_OR: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 || stk[sp] != 0.0) ? 1.0 : 0.0; break;
+      case AMWG_OP_NOT: stk[sp - 1] = stk[sp - 1] != 0.0 ? 0.0 : 1.0; break;
+      case AMWG_OP_SELECT: sp -= 2; stk[sp - 1] = stk[sp - 1] != 0.0 ? stk[sp] : stk[sp + 1]; break;
+      case AMWG_OP_LGAMMA: stk[sp - 1] = ld_lgamma(stk[sp - 1]); break;
+      case AMWG_OP_LFACTORIAL: stk[sp - 1] = ld_lfactorial(stk[sp - 1]); break;
+      case AMWG_OP_LCHOOSE: sp--; stk[sp - 1] = ld_lchoose(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LBETA: sp--; stk[sp - 1] = ld_lbeta(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LD_NORM: sp -= 2; stk[sp - 1] = ld_norm(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_UNIF: sp -= 2; stk[sp - 1] = ld_unif(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_BETA: sp -= 2; stk[sp - 1] = ld_beta(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_BERN: sp--; stk[sp - 1] = ld_bern(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LD_POIS: sp--; stk[sp - 1] = ld_pois(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LD_CAUCHY: sp -= 2; stk[sp - 1] = ld_cauchy(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_LAPLACE: sp -= 2; stk[sp - 1] = ld_laplace(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_GAMMA: sp -= 2; stk[sp - 1] = ld_gamma(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_INVGAMMA: sp -= 2; stk[sp - 1] = ld_invgamma(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_LNORM: sp -= 2; stk[sp - 1] = ld_lnorm(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_PARETO: sp -= 2; stk[sp - 1] = ld_pareto(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_T: sp -= 3; stk[sp - 1] = ld_t(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); break;
+      case AMWG_OP_LD_WEIBULL: sp -= 2; stk[sp - 1] = ld_weibull(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_LOGIS: sp -= 2; stk[sp - 1] = ld_logis(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_EXP: sp--; stk[sp - 1] = ld_exp(stk[sp - 1], stk[sp]); break;
+      case AMWG_OP_LD_BINOM: sp -= 2; stk[sp - 1] = ld_binom(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_NBINOM: sp -= 2; stk[sp - 1] = ld_nbinom(stk[sp - 1], stk[sp], stk[sp + 1]); break;
+      case AMWG_OP_LD_HYPER: sp -= 3; stk[sp - 1] = ld_hyper(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); break;
+      case AMWG_OP_ACC: lp = lp + stk[--sp]; break;
+      case AMWG_OP_PLATE: {
+        switch (ctx.plates[a].kind) {
+          case AMWG_PLATE_NORM_IID: sp -= 2; lp = lp + plate_norm_iid(ctx, a, stk[sp], stk[sp + 1]); break;
+          case AMWG_PLATE_BERN_IID: sp -= 1; lp = plate_bern_iid(ctx, a, stk[sp], lp); break;
+          case AMWG_PLATE_NORM_GROUPED: sp -= 1; lp = lp + plate_norm_grouped(ctx, a, es, stk[sp]); break;
+          case AMWG_PLATE_POIS_LOGLIN: lp = lp + plate_pois_loglin(ctx, a, es); break;
+          default: break;
+        }
+        break;
+      }
+      case AMWG_OP_LOOP_BEGIN: {
+        int skip_to = ctx.code[pc++];
+        loop_i = 0; loop_n = ctx.plates[a].n;
+        if (loop_n <= 0) pc = skip_to;
+        break;
+      }
+      case AMWG_OP_LOOP_END: lp = lp + stk[--sp]; if (++loop_i < loop_n) pc = a; else loop_i = 0; break;
+      case AMWG_OP_STORE: der[a] = stk[--sp]; break;
+      default:   // AMWG_OP_END
+        return (want_top && sp > 0) ? stk[sp - 1] : lp;
     }
-    break;  // END
-  }
-  return lp;
-}
-
-// derived quantities (state keys the model adds, mcmc.js:961-963, 990-995): program of <expr> STORE d
-__device__ __noinline__ void eval_derived(const Ctx& ctx, const EvalState& es, int pc, double* der) {
-  double stk[kStack];
-  int sp = 0;
-  for (;;) {
-    int w = ctx.code[pc++];
-    int op = w & 0xff, a = w >> 8;
-    if (exec_basic(ctx, es, op, a, pc, stk, sp, 0)) continue;
-    if (op == AMWG_OP_STORE) { der[a] = stk[--sp]; continue; }
-    break;
   }
 }
 
-// ---- K0: place every chain at init and evaluate log_post once (Sampler ctor, mcmc.js:954-963) -------------------------
+__device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) { return run_program(ctx, es, pc, nullptr, false); }
+
+// ---- K0: constant folding (amwg_model.fold_*), then place every chain at init and evaluate log_post once (mcmc.js:954-963) ---
+__global__ void amwg_fold_kernel(ModelDev m, int n_fold, const int* __restrict__ fold_prog, const int* __restrict__ fold_dst) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double* consts_global = reinterpret_cast<double*>(const_cast<unsigned char*>(m.image) + m.off_consts);
+  double* consts_smem = const_cast<double*>(ctx.consts);
+  EvalState es{nullptr, 0, -1, 0.0};
+  for (int k = 0; k < n_fold; ++k) {          // in order: later folds may use earlier ones
+    double v = run_program(ctx, es, fold_prog[k], nullptr, true);
+    consts_global[fold_dst[k]] = v;
+    consts_smem[fold_dst[k]] = v;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainArrays a, const double* __restrict__ init,
                                                             const double* __restrict__ pls0) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -337,6 +353,7 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
   for (int c = 0; c < m.D; ++c) {
     a.state[(unsigned long long)c * a.C + chain] = init[c];
     a.pls[(unsigned long long)c * a.C + chain] = pls0[c];
+    a.psd[(unsigned long long)c * a.C + chain] = js_exp(pls0[c]);
     a.acc[(unsigned long long)c * a.C + chain] = 0;
   }
   unsigned long long perm = 0;
@@ -358,7 +375,7 @@ __global__ void __launch_bounds__(kThreads) amwg_sweep_kernel(ModelDev m, ChainA
   if (chain >= a.C) return;
   const unsigned long long C = a.C;
   double* st = a.state + chain;
-  double* pls = a.pls + chain;
+  const double* psd = a.psd + chain;
   int* acc = a.acc + chain;
 
   RandomStream g;
@@ -382,7 +399,7 @@ __global__ void __launch_bounds__(kThreads) amwg_sweep_kernel(ModelDev m, ChainA
           if (e < m.D) {
             v = st[(unsigned long long)e * C];
           } else {
-            if (!have_der) { EvalState es{st, C, -1, 0.0}; eval_derived(ctx, es, m.derived_prog, der); have_der = true; }
+            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_program(ctx, es, m.derived_prog, der, false); have_der = true; }
             v = der[e - m.D];
           }
           sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
@@ -420,7 +437,7 @@ __global__ void __launch_bounds__(kThreads) amwg_sweep_kernel(ModelDev m, ChainA
           need = true;
         } else {
           // generate_proposal (mcmc.js:519, 577-579 / 596-598) and the bounds check (:520)
-          prop = js_rnorm(g, cur, js_exp(pls[ci]));
+          prop = js_rnorm(g, cur, psd[ci]);
           if (pa.type == AMWG_INT) prop = js_round(prop);
           need = !(prop < pa.lower || prop > pa.upper);
         }
@@ -472,7 +489,9 @@ __global__ void __launch_bounds__(256) amwg_adapt_kernel(ChainArrays a, AdaptArg
     unsigned long long idx = (unsigned long long)(ad.c0 + k) * a.C + chain;
     double rate = (double)a.acc[idx] / ad.batch_size[k];
     double ls = a.pls[idx];
-    a.pls[idx] = (rate > ad.target[k]) ? ls + ad.delta[k] : ls - ad.delta[k];
+    ls = (rate > ad.target[k]) ? ls + ad.delta[k] : ls - ad.delta[k];
+    a.pls[idx] = ls;
+    a.psd[idx] = js_exp(ls);          // the proposal sd of the next batch: Math.exp(prop_log_scale), mcmc.js:578
     a.acc[idx] = 0;
   }
 }
@@ -487,22 +506,20 @@ __global__ void __launch_bounds__(kThreads) amwg_derived_kernel(ModelDev m, Chai
   if (chain >= a.C) return;
   double der[kMaxDerived];
   EvalState es{a.state + chain, a.C, -1, 0.0};
-  eval_derived(ctx, es, m.derived_prog, der);
+  run_program(ctx, es, m.derived_prog, der, false);
   for (int d = 0; d < m.n_derived; ++d) out[(unsigned long long)d * a.C + chain] = der[d];
 }
 
-// ---- primitives for the parity tests ---------------------------------------------------------------------------------------
-__global__ void amwg_ld_kernel(int op, const double* __restrict__ args, int arity, long long n, double* __restrict__ out) {
+// ---- primitives for the parity tests / the `ld` host module ---------------------------------------------------------------
+// one row of arguments -> one ld.* value, through the same interpreter (program: CONST 0..arity-1, <op>, END in `code`)
+__global__ void amwg_ld_kernel(const int* __restrict__ code, const double* __restrict__ args, int arity, long long n, double* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  double stk[kStack];
-  int sp = 0;
-  for (int k = 0; k < arity; ++k) stk[sp++] = args[i * arity + k];
   Ctx ctx{};
+  ctx.code = code;
+  ctx.consts = args + i * arity;
   EvalState es{nullptr, 0, -1, 0.0};
-  int pc = 0;
-  exec_basic(ctx, es, op, 0, pc, stk, sp, 0);
-  out[i] = stk[sp - 1];
+  out[i] = run_program(ctx, es, 0, nullptr, true);
 }
 
 __global__ void amwg_primitive_kernel(int kind, const double* __restrict__ x, long long n, unsigned long long seed,
@@ -597,6 +614,9 @@ static int validate_model(const amwg_model* md) {
   if (D != md->n_comp) return fail("amwg_create: n_comp does not match the parameter list");
   if (md->logpost_prog < 0 || md->logpost_prog >= md->n_code) return fail("amwg_create: logpost_prog out of range");
   if (md->n_derived > 0 && (md->derived_prog < 0 || md->derived_prog >= md->n_code)) return fail("amwg_create: derived_prog out of range");
+  for (int k = 0; k < md->n_fold; ++k)
+    if (md->fold_prog[k] < 0 || md->fold_prog[k] >= md->n_code || md->fold_dst[k] < 0 || md->fold_dst[k] >= md->n_consts)
+      return fail("amwg_create: constant-folding table out of range");
   return 0;
 }
 
@@ -675,6 +695,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   s->smem_bytes = smem_used;
   if (cudaFuncSetAttribute(amwg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
     return bail(fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
 
@@ -684,7 +705,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   ChainArrays& a = s->a;
   a.C = n_chains; a.first_chain = first_chain; a.seed = seed;
   size_t DC = (size_t)s->D * (size_t)n_chains;
-  if (dev_alloc(s, DC, &a.state) || dev_alloc(s, DC, &a.pls) || dev_alloc(s, DC, &a.acc) || dev_alloc(s, (size_t)n_chains, &a.curr_lp) ||
+  if (dev_alloc(s, DC, &a.state) || dev_alloc(s, DC, &a.pls) || dev_alloc(s, DC, &a.psd) || dev_alloc(s, DC, &a.acc) || dev_alloc(s, (size_t)n_chains, &a.curr_lp) ||
       dev_alloc(s, (size_t)n_chains, &a.perm) || dev_alloc(s, (size_t)n_chains, &a.rng_n))
     return bail(-1);
 
@@ -693,6 +714,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   for (int c = 0; c < s->D; ++c) pls0[c] = s->opts[c].prop_log_scale;
   if (dev_upload(s, md->init, (size_t)s->D, &d_init) || dev_upload(s, pls0.data(), (size_t)s->D, &d_pls0)) return bail(-1);
 
+  if (md->n_fold > 0) {
+    int *d_fp = nullptr, *d_fd = nullptr;
+    if (dev_upload(s, md->fold_prog, (size_t)md->n_fold, &d_fp) || dev_upload(s, md->fold_dst, (size_t)md->n_fold, &d_fd)) return bail(-1);
+    amwg_fold_kernel<<<1, 32, s->smem_bytes, s->stream>>>(m, md->n_fold, d_fp, d_fd);
+    s->launches++;
+  }
   amwg_init_kernel<<<grid_for(n_chains, kThreads), kThreads, s->smem_bytes, s->stream>>>(m, a, d_init, d_pls0);
   s->launches++;
   cudaError_t e = cudaGetLastError();
@@ -887,16 +914,26 @@ extern "C" int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64
   if (n <= 0) return 0;
   if (op <= AMWG_OP_END || op >= AMWG_OP_ACC || arity < 1 || arity > 4) return fail("amwg_ld_eval: bad opcode or arity");
   CUDA_TRY(cudaSetDevice(device));
+  int code[8];
+  int nc = 0;
+  for (int k = 0; k < arity; ++k) code[nc++] = (k << 8) | AMWG_OP_CONST;
+  code[nc++] = op;
+  code[nc++] = AMWG_OP_END;
   double *d_args = nullptr, *d_out = nullptr;
+  int* d_code = nullptr;
   CUDA_TRY(cudaMalloc(&d_args, sizeof(double) * (size_t)n * arity));
-  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(d_args); return fail("amwg_ld_eval: cudaMalloc failed"); }
+  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess || cudaMalloc(&d_code, sizeof(code)) != cudaSuccess) {
+    cudaFree(d_args); cudaFree(d_out);
+    return fail("amwg_ld_eval: cudaMalloc failed");
+  }
   cudaError_t e = cudaMemcpy(d_args, args, sizeof(double) * (size_t)n * arity, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(d_code, code, sizeof(code), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    amwg_ld_kernel<<<(unsigned)((n + 127) / 128), 128>>>(op, d_args, arity, n, d_out);
+    amwg_ld_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_code, d_args, arity, n, d_out);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
-  cudaFree(d_args); cudaFree(d_out);
+  cudaFree(d_args); cudaFree(d_out); cudaFree(d_code);
   if (e != cudaSuccess) return fail(std::string("amwg_ld_eval: ") + cudaGetErrorString(e));
   return 0;
 }

@@ -7,11 +7,12 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <math_constants.h>
 
 namespace amwg {
 
 // ---- Math.log : the fdlibm e_log algorithm (what V8's ieee754::log implements) -------------------
-__device__ __forceinline__ double js_log(double x) {
+__device__ __noinline__ double js_log(double x) {
   const double ln2_hi = 6.93147180369123816490e-01, ln2_lo = 1.90821492927058770002e-10,
                two54 = 1.80143985094819840000e+16,
                Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
@@ -58,7 +59,7 @@ __device__ __forceinline__ double js_log(double x) {
 }
 
 // ---- Math.exp : the fdlibm e_exp algorithm ---------------------------------------------------------
-__device__ __forceinline__ double js_exp(double x) {
+__device__ __noinline__ double js_exp(double x) {
   const double huge = 1.0e+300, twom1000 = 9.33263618503218878990e-302,
                o_threshold = 7.09782712893383973096e+02, u_threshold = -7.45133219101941108420e+02,
                ln2HI = 6.93147180369123816490e-01, ln2LO = 1.90821492927058770002e-10,
@@ -137,6 +138,13 @@ __device__ __forceinline__ double u53(uint32_t a, uint32_t b) {
   return ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) * (1.0 / 9007199254740992.0);
 }
 
+// one Philox block = uniforms #2*blk and #2*blk+1 of chain (g0,g1). Kept out of line: it is ~80 instructions and
+// is needed at several points of a sweep; inlining it everywhere bloats the kernel past the instruction cache.
+__device__ __noinline__ double2 philox_uniform_pair(uint32_t blk_lo, uint32_t blk_hi, uint32_t g0, uint32_t g1, uint32_t k0, uint32_t k1) {
+  Philox4 p = philox4x32_10(blk_lo, blk_hi, g0, g1, k0, k1);
+  return make_double2(u53(p.r0, p.r1), u53(p.r2, p.r3));
+}
+
 struct RandomStream {
   uint32_t k0, k1, g0, g1;
   uint64_t n;          // index of the next Math.random() call of this chain
@@ -153,9 +161,9 @@ struct RandomStream {
       u = spare; has_spare = false;
     } else {
       uint64_t blk = n >> 1;
-      Philox4 p = philox4x32_10((uint32_t)blk, (uint32_t)(blk >> 32), g0, g1, k0, k1);
-      if (n & 1) { u = u53(p.r2, p.r3); }
-      else { u = u53(p.r0, p.r1); spare = u53(p.r2, p.r3); has_spare = true; }
+      double2 p = philox_uniform_pair((uint32_t)blk, (uint32_t)(blk >> 32), g0, g1, k0, k1);
+      if (n & 1) { u = p.y; }
+      else { u = p.x; spare = p.y; has_spare = true; }
     }
     ++n;
     return u;

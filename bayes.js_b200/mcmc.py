@@ -366,9 +366,9 @@ class AmwgSampler(Sampler):
         plates = (AmwgPlate * max(len(prog.plates), 1))()
         for k, pl in enumerate(prog.plates):
             q = AmwgPlate()
-            q.kind, q.n, q.body_prog = pl["kind"], pl["n"], pl["body_prog"]
+            q.kind, q.n = pl["kind"], pl["n"]
             for j in range(4):
-                q.col[j] = pl["col"][j]; q.arg_prog[j] = pl["arg_prog"][j]; q.iparam[j] = pl["iparam"][j]
+                q.col[j] = pl["col"][j]; q.iparam[j] = pl["iparam"][j]
             plates[k] = q
         m = AmwgModel()
         m.abi_version = _ffi.ABI_VERSION
@@ -380,7 +380,12 @@ class AmwgSampler(Sampler):
         m.n_consts, m.consts = consts.size, consts.ctypes.data_as(C.POINTER(C.c_double))
         m.n_columns, m.columns = len(prog.columns), cols
         m.n_plates, m.plates = len(prog.plates), plates
-        self._model_keepalive = (prm, init, opts, code, consts, cols, plates, m)
+        fold_prog = np.asarray(prog.fold_prog if prog.fold_prog else [0], dtype=np.int32)
+        fold_dst = np.asarray(prog.fold_dst if prog.fold_dst else [0], dtype=np.int32)
+        m.n_fold = len(prog.fold_prog)
+        m.fold_prog = fold_prog.ctypes.data_as(C.POINTER(C.c_int32))
+        m.fold_dst = fold_dst.ctypes.data_as(C.POINTER(C.c_int32))
+        self._model_keepalive = (prm, init, opts, code, consts, cols, plates, fold_prog, fold_dst, m)
         L = _ffi.lib()
         h = C.c_void_p()
         rc = L.amwg_create(C.byref(m), self.local_chains, self.first_chain, self.seed, self.device, C.byref(h))

@@ -288,7 +288,7 @@ _ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, 
 
 
 class Program:
-    """The lowered model: everything amwg_model needs, as numpy arrays."""
+    """The lowered model: everything amwg_model needs."""
 
     def __init__(self):
         self.code: List[int] = []
@@ -299,6 +299,8 @@ class Program:
         self.logpost_prog = 0
         self.derived_prog = -1
         self.derived_names: List[str] = []
+        self.fold_prog: List[int] = []         # word offsets of constant sub-expression programs (evaluated once on the device)
+        self.fold_dst: List[int] = []          # ... and the consts[] slot each one fills
         self.summary: List[str] = []           # human-readable: what each term became
 
     def const(self, v: float) -> int:
@@ -309,6 +311,10 @@ class Program:
             self.consts.append(float(v))
             self._const_index[key] = k
         return k
+
+    def fold_slot(self) -> int:
+        self.consts.append(float("nan"))       # filled by amwg_fold_kernel at create
+        return len(self.consts) - 1
 
     def emit(self, op: str, operand: int = 0, *extra: int):
         self.code.append((int(operand) << 8) | OP[op])
@@ -367,6 +373,64 @@ class Tracer:
             else:
                 st[name] = ParamVec(self, offsets[name], tuple(dim))
         return st
+
+
+# ---- ld.* as the JS source spells them (distributions.js), in device primitives ------------------------------------
+# A recorded LD_* node keeps its identity for plate recognition; when it is emitted as a scalar term or inside a
+# generic plate body it is first expanded into exactly the operations of the JS function, so that sub-expressions
+# without parameters (log(2*pi), log(sd) of a constant sd, lbeta(2,2) ...) can be folded to constants. Same operations,
+# same order => same bits as the native LD_* opcode.
+_NEG_INF = float("-inf")
+
+
+def _c(v) -> Sym:
+    return Sym("CONST", (), float(v))
+
+
+def _or(a: Sym, b: Sym) -> Sym:
+    return Sym("OR", (a, b))
+
+
+def _expand_ld(op: str, a: Tuple[Sym, ...]) -> Optional[Sym]:
+    log = Math.log
+    if op == "LD_NORM":                                   # distributions.js:119-121
+        x, mean, sd = a
+        return _c(-0.5) * log(_c(2) * _c(Math.PI)) - log(sd) - Math.pow(x - mean, 2) / (_c(2) * sd * sd)
+    if op == "LD_UNIF":                                   # :221-223
+        x, mn, mx = a
+        return where(_or(x < mn, x > mx), _NEG_INF, log(_c(1) / (mx - mn)))
+    if op == "LD_BETA":                                   # :104-113
+        x, s1, s2 = a
+        body = (s1 - 1) * log(x) + (s2 - 1) * log(_c(1) - x) - Sym("LBETA", (s1, s2))
+        return where(_or(x > 1, x < 0), _NEG_INF, where(Sym("AND", (s1 == 1, s2 == 1)), 0.0, body))
+    if op == "LD_BERN":                                   # :228-230
+        x, p = a
+        return where(Sym("NOT", (_or(x == 0, x == 1),)), _NEG_INF, log(x * p + (_c(1) - x) * (_c(1) - p)))
+    if op == "LD_POIS":                                   # :282-284
+        x, lam = a
+        return where(x < 0, _NEG_INF, log(lam) * x - lam - Sym("LFACTORIAL", (x,)))
+    if op == "LD_EXP":                                    # :217-219
+        x, rate = a
+        return where(x < 0, _NEG_INF, log(rate) - rate * x)
+    if op == "LD_LAPLACE":                                # :136-138
+        x, loc, scale = a
+        return (-abs(x - loc) / scale) - log(_c(2) * scale)
+    if op == "LD_CAUCHY":                                 # :115-117
+        x, loc, scale = a
+        return log(scale) - log(Math.pow(x - loc, 2) + Math.pow(scale, 2)) - log(_c(Math.PI))
+    return None                                           # the rest stay native opcodes
+
+
+def expand(node: Sym) -> Sym:
+    """Rewrite expandable LD_* nodes into primitives (iteratively bottom-up; trees are shallow)."""
+    if not node.args:
+        return node
+    args = tuple(expand(a) for a in node.args)
+    if node.op.startswith("LD_"):
+        e = _expand_ld(node.op, args)
+        if e is not None:
+            return e
+    return Sym(node.op, args, node.val)
 
 
 def _spine_terms(expr: Sym) -> List[Sym]:
@@ -434,16 +498,53 @@ class Lowering:
         self.n_comp = n_comp
         self.prog = Program()
         self.prog.columns = tracer.columns       # shared list: synthesized columns are appended
+        self._fold_memo: Dict[tuple, int] = {}
+        self._fold_trees: List[Tuple[int, Sym]] = []
+
+    # -- constant folding ---------------------------------------------------------------------------
+    def _key(self, n: Sym):
+        if n.op == "CONST": return ("K", np.float64(n.val).tobytes())
+        if n.op in ("COMP", "DATA", "DATA_I", "COMP_I", "FOLD"): return (n.op, n.val)
+        return (n.op,) + tuple(self._key(a) for a in n.args)
+
+    def fold(self, node: Sym) -> Sym:
+        """Replace every maximal parameter-free sub-expression that contains at least one operation by a FOLD(k) leaf;
+        consts[k] is computed once on the device (amwg_fold_kernel) with the device's own log/exp."""
+        def rec(n: Sym):
+            if n.op in ("CONST", "DATA", "FOLD"):
+                return n, True
+            if n.op in ("COMP", "DATA_I", "COMP_I"):
+                return n, False
+            parts = [rec(a) for a in n.args]
+            if all(c for _, c in parts):
+                return Sym(n.op, tuple(x for x, _ in parts), n.val), True
+            new_args = tuple(self._to_fold(x) if (c and x.args) else x for x, c in parts)
+            return Sym(n.op, new_args, n.val), False
+        out, is_const = rec(node)
+        return self._to_fold(out) if (is_const and out.args) else out
+
+    def _to_fold(self, tree: Sym) -> Sym:
+        key = self._key(tree)
+        k = self._fold_memo.get(key)
+        if k is None:
+            k = self.prog.fold_slot()
+            self._fold_memo[key] = k
+            self._fold_trees.append((k, tree))
+        return Sym("FOLD", (), k)
 
     # -- expressions ------------------------------------------------------------------------------
-    def emit_expr(self, node: Sym):
-        """Postfix emission, iterative (terms are shallow but plates bodies may hold long dot products)."""
+    def emit_expr(self, node: Sym, prepare: bool = True):
+        """Postfix emission (iterative). `prepare`: expand LD_* into primitives and fold constants first."""
+        if prepare:
+            node = self.fold(expand(node))
         p = self.prog
         work: List[Tuple[Sym, bool]] = [(node, False)]
         while work:
             n, done = work.pop()
             if n.op == "CONST":
                 p.emit("CONST", p.const(n.val)); continue
+            if n.op == "FOLD":
+                p.emit("CONST", n.val); continue
             if n.op == "COMP":
                 p.emit("COMP", n.val); continue
             if n.op == "DATA":
@@ -460,33 +561,22 @@ class Lowering:
             for a in reversed(n.args):
                 work.append((a, False))
 
-    def emit_subprogram(self, node: Sym) -> int:
-        """An END-terminated operand program placed after the main program; returns its word offset."""
-        start = len(self._tail)
-        saved, self.prog.code = self.prog.code, []
-        self.emit_expr(node)
-        self.prog.emit("END")
-        self._tail.extend(self.prog.code)
-        self.prog.code = saved
-        return start                         # relative to tail start; fixed up in finish()
-
     # -- plates -----------------------------------------------------------------------------------
-    def _make_plate(self, body: Sym, n: int) -> int:
-        """Register a plate for `body` (uses DATA_I/COMP_I with stride/offset) over n points; returns plate id."""
+    def _emit_plate(self, body: Sym, n: int):
+        """Emit the code for a plate over n points whose per-point term is `body` (uses DATA_I/COMP_I)."""
         p = self.prog
-        pl = dict(kind=PLATE_GENERIC, n=n, col=[-1] * 4, arg_prog=[-1] * 4, iparam=[0] * 4, body_prog=-1)
+        pl = dict(kind=PLATE_GENERIC, n=n, col=[-1] * 4, iparam=[0] * 4)
 
         def data_i(node, stride=1):
             return node.op == "DATA_I" and node.val[2] == stride
 
-        # ld.norm(data[i], mean, sd) with index-free mean/sd
+        q = len(p.plates)
         if body.op == "LD_NORM" and data_i(body.args[0]) and _index_free(body.args[2]):
             x, mean, sd = body.args
             if _index_free(mean):
                 pl.update(kind=PLATE_NORM_IID)
                 pl["col"][0] = x.val[0]; pl["iparam"][2] = x.val[1]
-                pl["arg_prog"][0] = self.emit_subprogram(mean)
-                pl["arg_prog"][1] = self.emit_subprogram(sd)
+                self.emit_expr(mean); self.emit_expr(sd)
                 p.summary.append(f"plate NORM_IID n={n}")
             elif mean.op == "COMP_I":
                 grp = self._grouped(mean, n)
@@ -495,12 +585,12 @@ class Lowering:
                     pl.update(kind=PLATE_NORM_GROUPED)
                     pl["col"][0] = x.val[0]; pl["col"][1] = start_col; pl["iparam"][2] = x.val[1]
                     pl["iparam"][0] = base; pl["iparam"][1] = J
-                    pl["arg_prog"][1] = self.emit_subprogram(sd)
+                    self.emit_expr(sd)
                     p.summary.append(f"plate NORM_GROUPED n={n} groups={J}")
         elif body.op == "LD_BERN" and data_i(body.args[0]) and _index_free(body.args[1]):
             pl.update(kind=PLATE_BERN_IID)
             pl["col"][0] = body.args[0].val[0]; pl["iparam"][2] = body.args[0].val[1]
-            pl["arg_prog"][0] = self.emit_subprogram(body.args[1])
+            self.emit_expr(body.args[1])
             p.summary.append(f"plate BERN_IID n={n}")
         elif body.op == "LD_POIS" and data_i(body.args[0]) and body.args[1].op == "EXP":
             lin = self._loglinear(body.args[1].args[0])
@@ -514,16 +604,18 @@ class Lowering:
                 pl["col"][1] = xcol; pl["col"][2] = self.t.add_column(lf)
                 pl["iparam"][0] = base; pl["iparam"][1] = K
                 p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
-        if pl["kind"] == PLATE_GENERIC:
-            saved, self.prog.code = self.prog.code, []
-            self.emit_expr(body)
-            self.prog.emit("END")
-            pl["body_prog"] = len(self._tail)
-            self._tail.extend(self.prog.code)
-            self.prog.code = saved
-            p.summary.append(f"plate GENERIC n={n} body={body.op}")
         p.plates.append(pl)
-        return len(p.plates) - 1
+        if pl["kind"] != PLATE_GENERIC:
+            p.emit("PLATE", q)
+            return
+        # generic: a bytecode loop, lp += body(i) in order
+        p.emit("LOOP_BEGIN", q, 0)
+        fix = len(p.code) - 1
+        body_start = len(p.code)
+        self.emit_expr(body)
+        p.emit("LOOP_END", body_start)
+        p.code[fix] = len(p.code)
+        p.summary.append(f"plate GENERIC n={n} body={body.op}")
 
     def _grouped(self, mean: Sym, n: int):
         """mu[g_i] with points sorted by group and groups covering a contiguous component range."""
@@ -556,7 +648,6 @@ class Lowering:
     # -- main -------------------------------------------------------------------------------------
     def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
         p = self.prog
-        self._tail: List[int] = []
         terms = _spine_terms(result)
         i = 0
         n_terms = len(terms)
@@ -564,15 +655,13 @@ class Lowering:
             tm = terms[i]
             pid = _has_plate_ref(tm)
             if pid is not None:                                   # symbolic-index term: a plate as written
-                q = self._make_plate(tm, self.t.plate_sizes[pid])
-                p.emit("PLATE", q)
+                self._emit_plate(tm, self.t.plate_sizes[pid])
                 i += 1
                 continue
             run = self._find_run(terms, i)
             if run is not None:
                 body, length = run
-                q = self._make_plate(body, length)
-                p.emit("PLATE", q)
+                self._emit_plate(body, length)
                 i += length
                 continue
             self.emit_expr(tm)
@@ -588,12 +677,12 @@ class Lowering:
                 p.emit("STORE", d)
                 p.derived_names.append(name)
             p.emit("END")
-        # operand programs live after the main programs
-        tail0 = len(p.code)
-        p.code.extend(self._tail)
-        for pl in p.plates:
-            pl["arg_prog"] = [a + tail0 if a >= 0 else -1 for a in pl["arg_prog"]]
-            if pl["body_prog"] >= 0: pl["body_prog"] += tail0
+        # constant sub-expression programs, in creation order (a later one may read an earlier slot)
+        for k, tree in self._fold_trees:
+            p.fold_prog.append(len(p.code))
+            p.fold_dst.append(k)
+            self.emit_expr(tree, prepare=False)
+            p.emit("END")
         p.logpost_prog = 0
         return p
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 1
+#define AMWG_ABI_VERSION 2
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -90,20 +90,24 @@ enum {
   AMWG_OP_LD_PARETO, AMWG_OP_LD_T, AMWG_OP_LD_WEIBULL, AMWG_OP_LD_LOGIS, AMWG_OP_LD_EXP,
   AMWG_OP_LD_BINOM, AMWG_OP_LD_NBINOM, AMWG_OP_LD_HYPER,
   AMWG_OP_ACC,          /* lp = lp + pop                                                     */
-  AMWG_OP_PLATE,        /* lp = plate[operand](lp)  : the O(N) likelihood sum                */
+  AMWG_OP_PLATE,        /* lp = plate[operand](lp, popped operands): a recognised O(N) likelihood sum */
   AMWG_OP_STORE,        /* derived[operand] = pop   (derived-quantity program only)          */
+  AMWG_OP_LOOP_BEGIN,   /* start of a GENERIC plate body: i = 0 (plate[operand].n points; skipped when n == 0) */
+  AMWG_OP_LOOP_END,     /* lp = lp + pop; if (++i < n) jump to word `operand` (first word of the body) */
   AMWG_OP__COUNT
 };
 
 /* A plate is a run of N structurally identical likelihood terms, `for (i...) log_post += ld.X(data[i], ...)`.
- * Recognised shapes get a hand-written inner loop; anything else runs its body program per point. */
+ * Recognised shapes get a hand-written inner loop (AMWG_OP_PLATE; their index-free operands are evaluated by
+ * the program and popped from the stack); anything else is a bytecode loop over its body
+ * (AMWG_OP_LOOP_BEGIN ... AMWG_OP_LOOP_END, body uses DATA_I / COMP_I), bit-faithful to the JS loop. */
 enum {
-  AMWG_PLATE_GENERIC = 0,   /* body program evaluated per point, lp += body(i) in order (bit-faithful)          */
-  AMWG_PLATE_NORM_IID,      /* sum_i ld.norm(x_i, mean, sd); mean, sd index-free.  Factorised:
-                               N*(-0.5*log(2pi) - log(sd)) - sum_i (x_i-mean)^2 / (2*sd*sd)   (KS-level parity) */
-  AMWG_PLATE_BERN_IID,      /* sum_i ld.bern(y_i, p); p index-free; sequential, bit-faithful                     */
-  AMWG_PLATE_NORM_GROUPED,  /* sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group                            */
-  AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k))                                        */
+  AMWG_PLATE_GENERIC = 0,   /* bytecode loop: lp += body(i), i = 0..n-1, in order                                   */
+  AMWG_PLATE_NORM_IID,      /* pops sd, mean.  sum_i ld.norm(x_i, mean, sd), factorised:
+                               N*(-0.5*log(2pi) - log(sd)) - sum_i (x_i-mean)^2 / (2*sd*sd)     (KS-level parity)   */
+  AMWG_PLATE_BERN_IID,      /* pops p.  sum_i ld.bern(y_i, p), sequential, bit-faithful                              */
+  AMWG_PLATE_NORM_GROUPED,  /* pops sd. sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group                      */
+  AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k))                                          */
 };
 
 typedef struct {
@@ -111,12 +115,8 @@ typedef struct {
   int32_t n;             /* number of points                                                       */
   int32_t col[4];        /* data columns: [0] x or y; GROUPED: [1] group start offsets (J+1);
                             POIS_LOGLIN: [1] X row-major n*K, [2] lfactorial(y) (filled by the host) */
-  int32_t arg_prog[4];   /* word offsets of index-free operand programs (END-terminated), -1 unused:
-                            NORM_*: [0] mean (IID only), [1] sd;  BERN: [0] p                        */
   int32_t iparam[4];     /* GROUPED: [0] first mu component, [1] J;  POIS_LOGLIN: [0] first beta component, [1] K;
                             all specialised kinds: [2] offset of the plate's first point inside col[0]              */
-  int32_t body_prog;     /* GENERIC: word offset of the per-point program (uses DATA_I / COMP_I)     */
-  int32_t _pad;
 } amwg_plate;
 
 typedef struct {
@@ -131,6 +131,10 @@ typedef struct {
   int32_t n_consts;   const double* consts;
   int32_t n_columns;  const amwg_column* columns;
   int32_t n_plates;   const amwg_plate* plates;
+  /* Constant sub-expressions (no parameter, no plate index) are evaluated ONCE on the device at create, with the
+   * device's own arithmetic, and stored into consts[fold_dst[k]]: fold_prog[k] is the word offset of an
+   * END-terminated expression program.  (log(2*pi), log(sd) of a constant sd, ... : same bits, computed once.) */
+  int32_t n_fold;     const int32_t* fold_prog;  const int32_t* fold_dst;
 } amwg_model;
 
 typedef struct amwg_sampler amwg_sampler;

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
 
 import __graft_entry__ as graft  # noqa: E402
 
+graft.load_package()          # registers `bayes_js_b200` (the directory name bayes.js_b200 is not an identifier)
+
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on a B200)")
@@ -29,7 +31,7 @@ def orc():
 def gpu_pkg(pkg):
     """The package with the CUDA library loaded; GPU tests fail loudly if the extension is missing."""
     lib = pkg._ffi.lib()
-    assert lib.amwg_abi_version() == 1
+    assert lib.amwg_abi_version() == 2
     return pkg
 
 

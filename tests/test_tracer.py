@@ -1,0 +1,172 @@
+"""Host logic (no GPU): the log_post tracer/lowering against the oracle's C models, evaluated with tests/prog_eval.py."""
+import numpy as np
+import pytest
+
+import models
+import prog_eval
+from conftest import NORM_DATA, PRESIDENTS, config2_data, config3_data
+
+
+def _trace(pkg, log_post, params, data):
+    mcmc = pkg.mcmc
+    cp = mcmc.complete_params(params)
+    offsets, n = {}, 0
+    for name, p in cp.items():
+        offsets[name] = n
+        n += int(np.prod(p["dim"]))
+    prog, derived = pkg.tracer.trace(log_post, cp, offsets, n, data)
+    return prog, derived, n
+
+
+def _oracle_logpost(orc, model, data, params, state):
+    s = orc.OracleSampler(model, data, params)
+    import ctypes
+    L = orc.lib()
+    st = np.array(list(state) + [0.0] * 4, dtype=np.float64)
+    fn = getattr(L, "orc_model_" + model)
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    dptr = ctypes.cast(ctypes.pointer(s._keep[-1]), ctypes.c_void_p) if s._keep[-1] is not None else None
+    return fn(st.ctypes.data, dptr, None), st
+
+
+def test_normal_model_becomes_two_terms_and_a_plate(pkg, orc):
+    prog, derived, n = _trace(pkg, models.norm_post_test(pkg.ld), models.PARAMS1, config2_data().tolist())
+    assert prog.summary == ["term LD_NORM", "term LD_UNIF", "plate NORM_IID n=1024"]
+    assert derived == ["var"] and n == 2
+    assert len(prog.fold_prog) >= 3                    # log(2pi)-log(100), 2*100*100, log(1/(100-0)) are computed once
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        st = [rng.normal(184, 3), rng.uniform(0.5, 20)]
+        ref, full = _oracle_logpost(orc, "norm_test", config2_data(), models.PARAMS1, st)
+        got = prog_eval.logpost(prog, consts, st, orc.lib())
+        assert abs(got - ref) <= 1e-12 * abs(ref)     # factorised plate: equal up to rounding
+        der = [None]
+        prog_eval.run(prog, consts, st, prog.derived_prog, orc.lib(), der=der)
+        assert der[0] == full[2] == st[1] * st[1]
+    # outside the support of the uniform prior: -Infinity, like ld.unif (distributions.js:221-223)
+    assert prog_eval.logpost(prog, consts, [184.0, 150.0], orc.lib()) == -np.inf
+
+
+def test_bernoulli_models_are_bit_faithful(pkg, orc):
+    y = config3_data()
+    prog, _, _ = _trace(pkg, models.spike_bern(pkg.ld, pkg.mcmc), models.PARAMS_SPIKE, {"x": y.tolist()})
+    assert prog.summary[-1] == "plate BERN_IID n=256"
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        st = [rng.uniform(-0.1, 1.1), float(rng.integers(0, 2))]
+        ref, _ = _oracle_logpost(orc, "spike_bern", {"x": y}, models.PARAMS_SPIKE, st)
+        got = prog_eval.logpost(prog, consts, st, orc.lib())
+        assert got == ref or (np.isnan(got) and np.isnan(ref)), (st, got, ref)
+        # evaluating "state with component c replaced" == evaluating the replaced state
+        assert prog_eval.logpost(prog, consts, [0.3, st[1]], orc.lib(), moved=0, val=st[0]) == got or np.isnan(got)
+
+
+def test_short_loops_stay_unrolled_and_generic_bodies_loop(pkg, orc):
+    ld = pkg.ld
+
+    def short(state, data):                         # 5 points: below the plate threshold
+        lp = 0
+        for i in range(len(data)):
+            lp += ld.norm(data[i], state.mu, state.sigma)
+        return lp
+    prog, _, _ = _trace(pkg, short, models.PARAMS_NORM, PRESIDENTS[:5])
+    assert prog.summary == ["term LD_NORM"] * 5
+
+    def cauchy_lik(state, data):                    # no specialised kernel for cauchy: bytecode loop
+        lp = ld.norm(state.mu, 0, 100) + ld.unif(state.sigma, 0, 100)
+        for i in range(len(data)):
+            lp += ld.cauchy(data[i], state.mu, state.sigma)
+        return lp
+    prog, _, _ = _trace(pkg, cauchy_lik, models.PARAMS_NORM, NORM_DATA)
+    assert prog.summary[-1] == "plate GENERIC n=10 body=LD_CAUCHY"
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    O = orc.lib()
+    st = [100.0, 30.0]
+    ref = O.orc_ld_norm(st[0], 0, 100) + O.orc_ld_unif(st[1], 0, 100)
+    for v in NORM_DATA:
+        ref = ref + O.orc_ld_cauchy(v, st[0], st[1])
+    assert prog_eval.logpost(prog, consts, st, O) == ref
+
+
+def test_symbolic_index_gives_the_same_program_as_the_concrete_loop(pkg):
+    ld, mcmc = pkg.ld, pkg.mcmc
+    data = config2_data().tolist()
+
+    def sym(state, d):
+        lp = ld.norm(state.mu, 0, 100) + ld.unif(state.sigma, 0, 100)
+        for i in mcmc.points(len(d)):
+            lp += ld.norm(d[i], state.mu, state.sigma)
+        return lp
+
+    def conc(state, d):
+        lp = ld.norm(state.mu, 0, 100) + ld.unif(state.sigma, 0, 100)
+        for i in range(len(d)):
+            lp += ld.norm(d[i], state.mu, state.sigma)
+        return lp
+    a, _, _ = _trace(pkg, sym, models.PARAMS_NORM, data)
+    b, _, _ = _trace(pkg, conc, models.PARAMS_NORM, data)
+    assert a.code == b.code and a.plates == b.plates and a.summary == b.summary
+
+
+def test_hierarchical_and_regression_plates(pkg, orc):
+    ld, mcmc = pkg.ld, pkg.mcmc
+    rng = np.random.default_rng(2)
+    J, per = 4, 16
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(100, 20, J)[g] + rng.normal(0, 5, J * per)
+
+    def hier(state, d):
+        lp = 0
+        for j in range(J):
+            lp += ld.norm(state.mu[j], 0, 100)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]], state.sigma)
+        return lp
+    params = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
+    prog, _, n = _trace(pkg, hier, params, {"y": y.tolist(), "g": g.tolist()})
+    assert n == J + 1
+    assert prog.summary[-J:] == [f"plate NORM_IID n={per}"] * J         # one plate per group: mu_j only touches its own
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    st = list(rng.normal(100, 20, J)) + [4.0]
+    ref, _ = _oracle_logpost(orc, "hier_norm", {"y": y, "g": g}, params, st)
+    assert abs(prog_eval.logpost(prog, consts, st, orc.lib()) - ref) <= 1e-12 * abs(ref)
+
+    K, n_pts = 3, 40
+    X = np.column_stack([np.ones(n_pts), rng.normal(0, 0.5, (n_pts, K - 1))])
+    beta_true = rng.normal(0, 0.3, K)
+    yy = rng.poisson(np.exp(X @ beta_true)).astype(float)
+
+    def poisreg(state, d):
+        lp = 0
+        for k in range(K):
+            lp += ld.norm(state.beta[k], 0, 10)
+        for i in mcmc.points(len(d.y)):
+            eta = 0
+            for k in range(K):
+                eta += d.X[i][k] * state.beta[k]
+            lp += ld.pois(d.y[i], mcmc.Math.exp(eta))
+        return lp
+    params = {"beta": {"type": "real", "dim": [K]}}
+    prog, _, _ = _trace(pkg, poisreg, params, {"y": yy.tolist(), "X": X.tolist()})
+    assert prog.summary[-1] == f"plate POIS_LOGLIN n={n_pts} K={K}"
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    st = list(rng.normal(0, 0.3, K))
+    ref, _ = _oracle_logpost(orc, "pois_reg", {"y": yy, "X": X}, params, st)
+    assert abs(prog_eval.logpost(prog, consts, st, orc.lib()) - ref) <= 1e-11 * abs(ref)
+
+
+def test_untraceable_closures_throw(pkg):
+    ld, mcmc = pkg.ld, pkg.mcmc
+
+    def branches(state, data):
+        if state.m == 0:                             # tests/test_data.js:163 pattern, written with a Python `if`
+            return ld.bern(1, 0.5)
+        return ld.bern(1, state.theta)
+    with pytest.raises(pkg.JsThrow, match="use mcmc.where"):
+        _trace(pkg, branches, models.PARAMS_SPIKE, None)
+    with pytest.raises(pkg.JsThrow, match="returned undefined"):
+        _trace(pkg, lambda s, d: None, models.PARAMS_NORM, None)
