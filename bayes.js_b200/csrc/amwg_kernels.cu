@@ -236,94 +236,141 @@ __device__ __noinline__ double plate_pois_loglin(const Ctx& ctx, int q, const Ev
 }
 
 // ---- the interpreter: ONE instance of the opcode switch in the whole library ---------------------------------------------
-// Runs the program at `pc` to its END.  log_post programs accumulate into lp (ACC / PLATE / LOOP_END) and return it;
-// expression programs (constant folding) return the top of stack; derived programs STORE into der[].
-__device__ __noinline__ double run_program(const Ctx& ctx, const EvalState& es, int pc, double* der, bool want_top) {
+// Runs the program at `pc` to its END (encoding: include/amwg.h).  log_post programs accumulate into lp (ACC flag / PLATE /
+// LOOP_END) and return it; expression programs (constant folding, ld.* evaluation) return the top of stack; derived programs
+// STORE into der[].  The program and the constants are read through 32-bit shared-memory addresses; the top of the stack
+// lives in a register, the rest in local memory (rarely touched: leaf operands are encoded inline).
+__device__ __forceinline__ unsigned lds_u32(unsigned saddr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
+__device__ __forceinline__ double lds_f64(unsigned saddr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr)); return v; }
+
+__device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalState& es, int pc,
+                                           double* der, bool want_top) {
   double stk[kStack];
+  double tos = 0.0;
   int sp = 0;
   double lp = 0.0;
   int loop_i = 0, loop_n = 0;
+#define AMWG_NEXT() ((int)lds_u32(code_sa + 4u * (unsigned)(pc++)))
+#define AMWG_POP(dst) do { dst = tos; --sp; tos = stk[sp]; } while (0)
+#define AMWG_OPND(dst, mode)                                                               \
+  do {                                                                                     \
+    if ((mode) == AMWG_MODE_STACK) { AMWG_POP(dst); }                                      \
+    else { int _ix = AMWG_NEXT(); dst = ((mode) == AMWG_MODE_CONST) ? lds_f64(consts_sa + 8u * (unsigned)_ix) : es.comp(_ix); } \
+  } while (0)
+#define AMWG_UN(expr) { double x; AMWG_OPND(x, mA); r = (expr); break; }
+#define AMWG_BIN(expr) { double x, y; AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
+#define AMWG_TER(expr) { double x, y, z; AMWG_OPND(z, mC); AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
+#define AMWG_QUA(expr) { double x, y, z, t; AMWG_OPND(t, mD); AMWG_OPND(z, mC); AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
   for (;;) {
-    const int w = ctx.code[pc++];
-    const int op = w & 0xff, a = w >> 8;
+    const unsigned w = (unsigned)AMWG_NEXT();
+    const int op = w & 0xff, mA = (w >> 8) & 3, mB = (w >> 10) & 3, mC = (w >> 12) & 3, mD = (w >> 14) & 3;
+    const bool acc = (w >> 16) & 1;
+    const int a = (int)(w >> 17);
+    double r = 0.0;
+    bool has_r = true;
     switch (op) {
-      case AMWG_OP_CONST: stk[sp++] = ctx.consts[a]; break;
-      case AMWG_OP_COMP: stk[sp++] = es.comp(a); break;
-      case AMWG_OP_DATA: stk[sp++] = ctx.col[a][ctx.code[pc++]]; break;
-      case AMWG_OP_DATA_I: { int off = ctx.code[pc++], stride = ctx.code[pc++]; stk[sp++] = ctx.col[a][off + stride * loop_i]; break; }
+      case AMWG_OP_CONST: r = lds_f64(consts_sa + 8u * (unsigned)a); break;
+      case AMWG_OP_COMP: r = es.comp(a); break;
+      case AMWG_OP_DATA: r = ctx.col[a][AMWG_NEXT()]; break;
+      case AMWG_OP_DATA_I: { int off = AMWG_NEXT(); int stride = AMWG_NEXT(); r = ctx.col[a][off + stride * loop_i]; break; }
       case AMWG_OP_COMP_I: {
-        int off = ctx.code[pc++], stride = ctx.code[pc++], base = ctx.code[pc++];
-        stk[sp++] = es.comp(base + (int)ctx.col[a][off + stride * loop_i]);
+        int off = AMWG_NEXT(); int stride = AMWG_NEXT(); int base = AMWG_NEXT();
+        r = es.comp(base + (int)ctx.col[a][off + stride * loop_i]);
         break;
       }
-      case AMWG_OP_ADD: sp--; stk[sp - 1] = stk[sp - 1] + stk[sp]; break;
-      case AMWG_OP_SUB: sp--; stk[sp - 1] = stk[sp - 1] - stk[sp]; break;
-      case AMWG_OP_MUL: sp--; stk[sp - 1] = stk[sp - 1] * stk[sp]; break;
-      case AMWG_OP_DIV: sp--; stk[sp - 1] = stk[sp - 1] / stk[sp]; break;
-      case AMWG_OP_NEG: stk[sp - 1] = -stk[sp - 1]; break;
-      case AMWG_OP_LOG: stk[sp - 1] = js_log(stk[sp - 1]); break;
-      case AMWG_OP_EXP: stk[sp - 1] = js_exp(stk[sp - 1]); break;
-      case AMWG_OP_SQRT: stk[sp - 1] = sqrt(stk[sp - 1]); break;
-      case AMWG_OP_ABS: stk[sp - 1] = fabs(stk[sp - 1]); break;
-      case AMWG_OP_POW: sp--; stk[sp - 1] = js_pow(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LT: sp--; stk[sp - 1] = stk[sp - 1] < stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_LE: sp--; stk[sp - 1] = stk[sp - 1] <= stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_GT: sp--; stk[sp - 1] = stk[sp - 1] > stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_GE: sp--; stk[sp - 1] = stk[sp - 1] >= stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_EQ: sp--; stk[sp - 1] = stk[sp - 1] == stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_NE: sp--; stk[sp - 1] = stk[sp - 1] != stk[sp] ? 1.0 : 0.0; break;
-      case AMWG_OP_AND: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 && stk[sp] != 0.0) ? 1.0 : 0.0; break;
-      case AMWG_OP_OR: sp--; stk[sp - 1] = (stk[sp - 1] != 0.0 || stk[sp] != 0.0) ? 1.0 : 0.0; break;
-      case AMWG_OP_NOT: stk[sp - 1] = stk[sp - 1] != 0.0 ? 0.0 : 1.0; break;
-      case AMWG_OP_SELECT: sp -= 2; stk[sp - 1] = stk[sp - 1] != 0.0 ? stk[sp] : stk[sp + 1]; break;
-      case AMWG_OP_LGAMMA: stk[sp - 1] = ld_lgamma(stk[sp - 1]); break;
-      case AMWG_OP_LFACTORIAL: stk[sp - 1] = ld_lfactorial(stk[sp - 1]); break;
-      case AMWG_OP_LCHOOSE: sp--; stk[sp - 1] = ld_lchoose(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LBETA: sp--; stk[sp - 1] = ld_lbeta(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LD_NORM: sp -= 2; stk[sp - 1] = ld_norm(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_UNIF: sp -= 2; stk[sp - 1] = ld_unif(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_BETA: sp -= 2; stk[sp - 1] = ld_beta(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_BERN: sp--; stk[sp - 1] = ld_bern(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LD_POIS: sp--; stk[sp - 1] = ld_pois(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LD_CAUCHY: sp -= 2; stk[sp - 1] = ld_cauchy(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_LAPLACE: sp -= 2; stk[sp - 1] = ld_laplace(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_GAMMA: sp -= 2; stk[sp - 1] = ld_gamma(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_INVGAMMA: sp -= 2; stk[sp - 1] = ld_invgamma(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_LNORM: sp -= 2; stk[sp - 1] = ld_lnorm(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_PARETO: sp -= 2; stk[sp - 1] = ld_pareto(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_T: sp -= 3; stk[sp - 1] = ld_t(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); break;
-      case AMWG_OP_LD_WEIBULL: sp -= 2; stk[sp - 1] = ld_weibull(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_LOGIS: sp -= 2; stk[sp - 1] = ld_logis(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_EXP: sp--; stk[sp - 1] = ld_exp(stk[sp - 1], stk[sp]); break;
-      case AMWG_OP_LD_BINOM: sp -= 2; stk[sp - 1] = ld_binom(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_NBINOM: sp -= 2; stk[sp - 1] = ld_nbinom(stk[sp - 1], stk[sp], stk[sp + 1]); break;
-      case AMWG_OP_LD_HYPER: sp -= 3; stk[sp - 1] = ld_hyper(stk[sp - 1], stk[sp], stk[sp + 1], stk[sp + 2]); break;
-      case AMWG_OP_ACC: lp = lp + stk[--sp]; break;
+      case AMWG_OP_ADD: AMWG_BIN(x + y)
+      case AMWG_OP_SUB: AMWG_BIN(x - y)
+      case AMWG_OP_MUL: AMWG_BIN(x * y)
+      case AMWG_OP_DIV: AMWG_BIN(x / y)
+      case AMWG_OP_NEG: AMWG_UN(-x)
+      case AMWG_OP_LOG: AMWG_UN(js_log(x))
+      case AMWG_OP_EXP: AMWG_UN(js_exp(x))
+      case AMWG_OP_SQRT: AMWG_UN(sqrt(x))
+      case AMWG_OP_ABS: AMWG_UN(fabs(x))
+      case AMWG_OP_POW: AMWG_BIN(js_pow(x, y))
+      case AMWG_OP_LT: AMWG_BIN(x < y ? 1.0 : 0.0)
+      case AMWG_OP_LE: AMWG_BIN(x <= y ? 1.0 : 0.0)
+      case AMWG_OP_GT: AMWG_BIN(x > y ? 1.0 : 0.0)
+      case AMWG_OP_GE: AMWG_BIN(x >= y ? 1.0 : 0.0)
+      case AMWG_OP_EQ: AMWG_BIN(x == y ? 1.0 : 0.0)
+      case AMWG_OP_NE: AMWG_BIN(x != y ? 1.0 : 0.0)
+      case AMWG_OP_AND: AMWG_BIN((x != 0.0 && y != 0.0) ? 1.0 : 0.0)
+      case AMWG_OP_OR: AMWG_BIN((x != 0.0 || y != 0.0) ? 1.0 : 0.0)
+      case AMWG_OP_NOT: AMWG_UN(x != 0.0 ? 0.0 : 1.0)
+      case AMWG_OP_SELECT: AMWG_TER(x != 0.0 ? y : z)
+      case AMWG_OP_LGAMMA: AMWG_UN(ld_lgamma(x))
+      case AMWG_OP_LFACTORIAL: AMWG_UN(ld_lfactorial(x))
+      case AMWG_OP_LCHOOSE: AMWG_BIN(ld_lchoose(x, y))
+      case AMWG_OP_LBETA: AMWG_BIN(ld_lbeta(x, y))
+      case AMWG_OP_LD_NORM: AMWG_TER(ld_norm(x, y, z))
+      case AMWG_OP_LD_UNIF: AMWG_TER(ld_unif(x, y, z))
+      case AMWG_OP_LD_BETA: AMWG_TER(ld_beta(x, y, z))
+      case AMWG_OP_LD_BERN: AMWG_BIN(ld_bern(x, y))
+      case AMWG_OP_LD_POIS: AMWG_BIN(ld_pois(x, y))
+      case AMWG_OP_LD_CAUCHY: AMWG_TER(ld_cauchy(x, y, z))
+      case AMWG_OP_LD_LAPLACE: AMWG_TER(ld_laplace(x, y, z))
+      case AMWG_OP_LD_GAMMA: AMWG_TER(ld_gamma(x, y, z))
+      case AMWG_OP_LD_INVGAMMA: AMWG_TER(ld_invgamma(x, y, z))
+      case AMWG_OP_LD_LNORM: AMWG_TER(ld_lnorm(x, y, z))
+      case AMWG_OP_LD_PARETO: AMWG_TER(ld_pareto(x, y, z))
+      case AMWG_OP_LD_T: AMWG_QUA(ld_t(x, y, z, t))
+      case AMWG_OP_LD_WEIBULL: AMWG_TER(ld_weibull(x, y, z))
+      case AMWG_OP_LD_LOGIS: AMWG_TER(ld_logis(x, y, z))
+      case AMWG_OP_LD_EXP: AMWG_BIN(ld_exp(x, y))
+      case AMWG_OP_LD_BINOM: AMWG_TER(ld_binom(x, y, z))
+      case AMWG_OP_LD_NBINOM: AMWG_TER(ld_nbinom(x, y, z))
+      case AMWG_OP_LD_HYPER: AMWG_QUA(ld_hyper(x, y, z, t))
+      case AMWG_OP_ACC: { double x; AMWG_POP(x); lp = lp + x; has_r = false; break; }
       case AMWG_OP_PLATE: {
+        has_r = false;
         switch (ctx.plates[a].kind) {
-          case AMWG_PLATE_NORM_IID: sp -= 2; lp = lp + plate_norm_iid(ctx, a, stk[sp], stk[sp + 1]); break;
-          case AMWG_PLATE_BERN_IID: sp -= 1; lp = plate_bern_iid(ctx, a, stk[sp], lp); break;
-          case AMWG_PLATE_NORM_GROUPED: sp -= 1; lp = lp + plate_norm_grouped(ctx, a, es, stk[sp]); break;
+          case AMWG_PLATE_NORM_IID: { double mean, sd; AMWG_OPND(sd, mB); AMWG_OPND(mean, mA); lp = lp + plate_norm_iid(ctx, a, mean, sd); break; }
+          case AMWG_PLATE_BERN_IID: { double p; AMWG_OPND(p, mA); lp = plate_bern_iid(ctx, a, p, lp); break; }
+          case AMWG_PLATE_NORM_GROUPED: { double sd; AMWG_OPND(sd, mA); lp = lp + plate_norm_grouped(ctx, a, es, sd); break; }
           case AMWG_PLATE_POIS_LOGLIN: lp = lp + plate_pois_loglin(ctx, a, es); break;
           default: break;
         }
         break;
       }
       case AMWG_OP_LOOP_BEGIN: {
-        int skip_to = ctx.code[pc++];
+        int skip_to = AMWG_NEXT();
         loop_i = 0; loop_n = ctx.plates[a].n;
         if (loop_n <= 0) pc = skip_to;
+        has_r = false;
         break;
       }
-      case AMWG_OP_LOOP_END: lp = lp + stk[--sp]; if (++loop_i < loop_n) pc = a; else loop_i = 0; break;
-      case AMWG_OP_STORE: der[a] = stk[--sp]; break;
+      case AMWG_OP_LOOP_END: {
+        int body = AMWG_NEXT();
+        double x; AMWG_POP(x);
+        lp = lp + x;
+        if (++loop_i < loop_n) pc = body; else loop_i = 0;
+        has_r = false;
+        break;
+      }
+      case AMWG_OP_STORE: { double x; AMWG_POP(x); der[a] = x; has_r = false; break; }
       default:   // AMWG_OP_END
-        return (want_top && sp > 0) ? stk[sp - 1] : lp;
+        return (want_top && sp > 0) ? tos : lp;
+    }
+    if (has_r) {
+      if (acc) lp = lp + r;
+      else { stk[sp] = tos; ++sp; tos = r; }
     }
   }
+#undef AMWG_NEXT
+#undef AMWG_POP
+#undef AMWG_OPND
+#undef AMWG_UN
+#undef AMWG_BIN
+#undef AMWG_TER
+#undef AMWG_QUA
 }
 
-__device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) { return run_program(ctx, es, pc, nullptr, false); }
+__device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
+  return run_program(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, nullptr, false);
+}
+__device__ __forceinline__ double run_ctx(const Ctx& ctx, const EvalState& es, int pc, double* der, bool want_top) {
+  return run_program(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, der, want_top);
+}
 
 // ---- K0: constant folding (amwg_model.fold_*), then place every chain at init and evaluate log_post once (mcmc.js:954-963) ---
 __global__ void amwg_fold_kernel(ModelDev m, int n_fold, const int* __restrict__ fold_prog, const int* __restrict__ fold_dst) {
@@ -336,7 +383,7 @@ __global__ void amwg_fold_kernel(ModelDev m, int n_fold, const int* __restrict__
   double* consts_smem = const_cast<double*>(ctx.consts);
   EvalState es{nullptr, 0, -1, 0.0};
   for (int k = 0; k < n_fold; ++k) {          // in order: later folds may use earlier ones
-    double v = run_program(ctx, es, fold_prog[k], nullptr, true);
+    double v = run_ctx(ctx, es, fold_prog[k], nullptr, true);
     consts_global[fold_dst[k]] = v;
     consts_smem[fold_dst[k]] = v;
   }
@@ -399,7 +446,7 @@ __global__ void __launch_bounds__(kThreads) amwg_sweep_kernel(ModelDev m, ChainA
           if (e < m.D) {
             v = st[(unsigned long long)e * C];
           } else {
-            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_program(ctx, es, m.derived_prog, der, false); have_der = true; }
+            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_ctx(ctx, es, m.derived_prog, der, false); have_der = true; }
             v = der[e - m.D];
           }
           sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
@@ -506,20 +553,29 @@ __global__ void __launch_bounds__(kThreads) amwg_derived_kernel(ModelDev m, Chai
   if (chain >= a.C) return;
   double der[kMaxDerived];
   EvalState es{a.state + chain, a.C, -1, 0.0};
-  run_program(ctx, es, m.derived_prog, der, false);
+  run_ctx(ctx, es, m.derived_prog, der, false);
   for (int d = 0; d < m.n_derived; ++d) out[(unsigned long long)d * a.C + chain] = der[d];
 }
 
 // ---- primitives for the parity tests / the `ld` host module ---------------------------------------------------------------
-// one row of arguments -> one ld.* value, through the same interpreter (program: CONST 0..arity-1, <op>, END in `code`)
-__global__ void amwg_ld_kernel(const int* __restrict__ code, const double* __restrict__ args, int arity, long long n, double* __restrict__ out) {
+// one row of arguments -> one ld.* value, through the same interpreter: program `<op A=const0 B=const1 ..> END`, the
+// row's arguments are the thread's private constants (staged in shared memory like a model's).
+__global__ void __launch_bounds__(128) amwg_ld_kernel(int word, int arity, const double* __restrict__ args, long long n, double* __restrict__ out) {
+  __shared__ int code[8];
+  __shared__ double consts[128 * 4];
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (threadIdx.x == 0) {
+    int nc = 0;
+    code[nc++] = word;
+    for (int k = arity - 1; k >= 0; --k) code[nc++] = k;      // inline operand words: last operand first
+    code[nc++] = AMWG_OP_END;
+  }
+  if (i < n) for (int k = 0; k < arity; ++k) consts[threadIdx.x * 4 + k] = args[i * arity + k];
+  __syncthreads();
   if (i >= n) return;
   Ctx ctx{};
-  ctx.code = code;
-  ctx.consts = args + i * arity;
   EvalState es{nullptr, 0, -1, 0.0};
-  out[i] = run_program(ctx, es, 0, nullptr, true);
+  out[i] = run_program(smem_u32(code), smem_u32(consts + threadIdx.x * 4), ctx, es, 0, nullptr, true);
 }
 
 __global__ void amwg_primitive_kernel(int kind, const double* __restrict__ x, long long n, unsigned long long seed,
@@ -912,28 +968,20 @@ extern "C" int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scal
 
 extern "C" int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device) {
   if (n <= 0) return 0;
-  if (op <= AMWG_OP_END || op >= AMWG_OP_ACC || arity < 1 || arity > 4) return fail("amwg_ld_eval: bad opcode or arity");
+  if (op <= AMWG_OP_COMP_I || op >= AMWG_OP_ACC || arity < 1 || arity > 4) return fail("amwg_ld_eval: bad opcode or arity");
   CUDA_TRY(cudaSetDevice(device));
-  int code[8];
-  int nc = 0;
-  for (int k = 0; k < arity; ++k) code[nc++] = (k << 8) | AMWG_OP_CONST;
-  code[nc++] = op;
-  code[nc++] = AMWG_OP_END;
+  const int c = AMWG_MODE_CONST;
+  int word = AMWG_WORD(op, c, arity > 1 ? c : 0, arity > 2 ? c : 0, arity > 3 ? c : 0, 0, 0);
   double *d_args = nullptr, *d_out = nullptr;
-  int* d_code = nullptr;
   CUDA_TRY(cudaMalloc(&d_args, sizeof(double) * (size_t)n * arity));
-  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess || cudaMalloc(&d_code, sizeof(code)) != cudaSuccess) {
-    cudaFree(d_args); cudaFree(d_out);
-    return fail("amwg_ld_eval: cudaMalloc failed");
-  }
+  if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(d_args); return fail("amwg_ld_eval: cudaMalloc failed"); }
   cudaError_t e = cudaMemcpy(d_args, args, sizeof(double) * (size_t)n * arity, cudaMemcpyHostToDevice);
-  if (e == cudaSuccess) e = cudaMemcpy(d_code, code, sizeof(code), cudaMemcpyHostToDevice);
   if (e == cudaSuccess) {
-    amwg_ld_kernel<<<(unsigned)((n + 127) / 128), 128>>>(d_code, d_args, arity, n, d_out);
+    amwg_ld_kernel<<<(unsigned)((n + 127) / 128), 128>>>(word, arity, d_args, n, d_out);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(out, d_out, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost);
-  cudaFree(d_args); cudaFree(d_out); cudaFree(d_code);
+  cudaFree(d_args); cudaFree(d_out);
   if (e != cudaSuccess) return fail(std::string("amwg_ld_eval: ") + cudaGetErrorString(e));
   return 0;
 }

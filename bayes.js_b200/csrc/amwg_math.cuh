@@ -145,28 +145,42 @@ __device__ __noinline__ double2 philox_uniform_pair(uint32_t blk_lo, uint32_t bl
   return make_double2(u53(p.r0, p.r1), u53(p.r2, p.r3));
 }
 
+// The chain's position in its Math.random() stream plus the Philox block that contains it.  Lanes of a warp sit at
+// different positions (rnorm consumes a data-dependent number of uniforms), so the block is fetched at ONE call site per
+// draw with a per-lane block index: divergence in stream position never multiplies the Philox work.
 struct RandomStream {
   uint32_t k0, k1, g0, g1;
   uint64_t n;          // index of the next Math.random() call of this chain
-  double spare;        // uniform #n when n is odd and the block was computed for n-1
-  bool has_spare;
+  uint64_t cb;         // index of the cached block (uniforms #2*cb, #2*cb+1), ~0 if none
+  double c0, c1;
 
   __device__ __forceinline__ void init(uint64_t seed, uint64_t chain, uint64_t pos) {
     k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); g0 = (uint32_t)chain; g1 = (uint32_t)(chain >> 32);
-    n = pos; has_spare = false; spare = 0.0;
+    n = pos; cb = ~0ull; c0 = c1 = 0.0;
   }
+  __device__ __forceinline__ void load(uint64_t blk) {
+    double2 p = philox_uniform_pair((uint32_t)blk, (uint32_t)(blk >> 32), g0, g1, k0, k1);
+    cb = blk; c0 = p.x; c1 = p.y;
+  }
+  // one uniform
   __device__ __forceinline__ double next() {
-    double u;
-    if ((n & 1) && has_spare) {
-      u = spare; has_spare = false;
-    } else {
-      uint64_t blk = n >> 1;
-      double2 p = philox_uniform_pair((uint32_t)blk, (uint32_t)(blk >> 32), g0, g1, k0, k1);
-      if (n & 1) { u = p.y; }
-      else { u = p.x; spare = p.y; has_spare = true; }
-    }
+    uint64_t blk = n >> 1;
+    if (cb != blk) load(blk);
+    double u = (n & 1) ? c1 : c0;
     ++n;
     return u;
+  }
+  // two consecutive uniforms (#n, #n+1) with exactly one block fetch: for odd n the first one is the cached block's
+  // second word and the new block provides the second one.
+  __device__ __forceinline__ void next2(double& u, double& v) {
+    if ((n & 1) && cb != (n >> 1)) load(n >> 1);          // only right after a kernel (re)start
+    double first_odd = c1;
+    uint64_t blk = (n + 1) >> 1;                          // even n: the block of n; odd n: the next block
+    bool odd = (n & 1);
+    load(blk);
+    u = odd ? first_odd : c0;
+    v = odd ? c0 : c1;
+    n += 2;
   }
 };
 
@@ -174,8 +188,9 @@ struct RandomStream {
 __device__ __forceinline__ double js_rnorm(RandomStream& g, double mean, double sd) {
   double u, v, x, y, q;
   do {
-    u = g.next();
-    v = 1.7156 * (g.next() - 0.5);
+    double r;
+    g.next2(u, r);
+    v = 1.7156 * (r - 0.5);
     x = u - 0.449871;
     y = fabs(v) + 0.386595;
     q = x * x + y * (0.19600 * y - 0.25472 * x);

@@ -279,6 +279,8 @@ class DataObject(dict):
 # tracing + lowering
 # ------------------------------------------------------------------------------------------------
 _MIN_PLATE = 8          # shorter runs stay unrolled scalar terms
+MAX_IMMEDIATE = 32767
+MODE_STACK, MODE_CONST, MODE_COMP = 0, 1, 2
 _ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, "SQRT": 1, "ABS": 1, "POW": 2,
           "LT": 2, "LE": 2, "GT": 2, "GE": 2, "EQ": 2, "NE": 2, "AND": 2, "OR": 2, "NOT": 1, "SELECT": 3,
           "LGAMMA": 1, "LFACTORIAL": 1, "LCHOOSE": 2, "LBETA": 2,
@@ -316,8 +318,13 @@ class Program:
         self.consts.append(float("nan"))       # filled by amwg_fold_kernel at create
         return len(self.consts) - 1
 
-    def emit(self, op: str, operand: int = 0, *extra: int):
-        self.code.append((int(operand) << 8) | OP[op])
+    def emit(self, op: str, operand: int = 0, *extra: int, modes=(0, 0, 0, 0), acc: bool = False):
+        """One instruction word (include/amwg.h): opcode | operand modes A..D | ACC flag | 15-bit immediate, + extra words."""
+        operand = int(operand)
+        if not 0 <= operand <= MAX_IMMEDIATE:
+            raise JsThrow("log_post is too large for the device program format (immediate > 32767)")
+        m = list(modes) + [0] * (4 - len(modes))
+        self.code.append(OP[op] | (m[0] << 8) | (m[1] << 10) | (m[2] << 12) | (m[3] << 14) | ((1 if acc else 0) << 16) | (operand << 17))
         self.code.extend(int(e) for e in extra)
 
 
@@ -533,33 +540,55 @@ class Lowering:
         return Sym("FOLD", (), k)
 
     # -- expressions ------------------------------------------------------------------------------
-    def emit_expr(self, node: Sym, prepare: bool = True):
-        """Postfix emission (iterative). `prepare`: expand LD_* into primitives and fold constants first."""
-        if prepare:
-            node = self.fold(expand(node))
+    def _inline(self, n: Sym):
+        """(mode, word) when the operand can ride inside the instruction: constants and state components."""
+        if n.op == "CONST": return MODE_CONST, self.prog.const(n.val)
+        if n.op == "FOLD": return MODE_CONST, n.val
+        if n.op == "COMP": return MODE_COMP, n.val
+        return None
+
+    def _operands(self, args):
+        """Emit the stack operands (left to right) and return (modes, inline words in consumption order: last operand first)."""
+        modes, words = [], []
+        for a in args:
+            il = self._inline(a)
+            if il is None:
+                self._emit(a, False)
+                modes.append(MODE_STACK)
+            else:
+                modes.append(il[0])
+                words.append(il[1])
+        return modes, list(reversed(words))
+
+    def _emit(self, n: Sym, acc: bool):
         p = self.prog
-        work: List[Tuple[Sym, bool]] = [(node, False)]
-        while work:
-            n, done = work.pop()
-            if n.op == "CONST":
-                p.emit("CONST", p.const(n.val)); continue
-            if n.op == "FOLD":
-                p.emit("CONST", n.val); continue
-            if n.op == "COMP":
-                p.emit("COMP", n.val); continue
-            if n.op == "DATA":
-                p.emit("DATA", n.val[0], n.val[1]); continue
-            if n.op == "DATA_I":
-                p.emit("DATA_I", n.val[0], n.val[1], n.val[2]); continue
-            if n.op == "COMP_I":
-                p.emit("COMP_I", n.val[0], n.val[1], n.val[2], n.val[3]); continue
-            if done:
-                p.emit(n.op); continue
+        if n.op in ("CONST", "FOLD", "COMP"):
+            mode, idx = self._inline(n)
+            p.emit("CONST" if mode == MODE_CONST else "COMP", idx, acc=acc)
+        elif n.op == "DATA":
+            p.emit("DATA", n.val[0], n.val[1], acc=acc)
+        elif n.op == "DATA_I":
+            p.emit("DATA_I", n.val[0], n.val[1], n.val[2], acc=acc)
+        elif n.op == "COMP_I":
+            p.emit("COMP_I", n.val[0], n.val[1], n.val[2], n.val[3], acc=acc)
+        else:
             if n.op not in _ARITY:
                 raise JsThrow(f"cannot lower operation {n.op}")
-            work.append((n, True))
-            for a in reversed(n.args):
-                work.append((a, False))
+            modes, words = self._operands(n.args)
+            p.emit(n.op, 0, *words, modes=modes, acc=acc)
+
+    def emit_expr(self, node: Sym, prepare: bool = True, acc: bool = False):
+        """Postfix emission. `prepare`: expand LD_* into primitives and fold constants first. `acc`: the value is
+        added to lp (a term of the sum) instead of being left on the stack."""
+        if prepare:
+            node = self.fold(expand(node))
+        import sys
+        if sys.getrecursionlimit() < 20000:
+            sys.setrecursionlimit(20000)
+        self._emit(node, acc)
+
+    def prepared(self, node: Sym) -> Sym:
+        return self.fold(expand(node))
 
     # -- plates -----------------------------------------------------------------------------------
     def _emit_plate(self, body: Sym, n: int):
@@ -571,12 +600,13 @@ class Lowering:
             return node.op == "DATA_I" and node.val[2] == stride
 
         q = len(p.plates)
+        operands: List[Sym] = []
         if body.op == "LD_NORM" and data_i(body.args[0]) and _index_free(body.args[2]):
             x, mean, sd = body.args
             if _index_free(mean):
                 pl.update(kind=PLATE_NORM_IID)
                 pl["col"][0] = x.val[0]; pl["iparam"][2] = x.val[1]
-                self.emit_expr(mean); self.emit_expr(sd)
+                operands = [mean, sd]
                 p.summary.append(f"plate NORM_IID n={n}")
             elif mean.op == "COMP_I":
                 grp = self._grouped(mean, n)
@@ -585,12 +615,12 @@ class Lowering:
                     pl.update(kind=PLATE_NORM_GROUPED)
                     pl["col"][0] = x.val[0]; pl["col"][1] = start_col; pl["iparam"][2] = x.val[1]
                     pl["iparam"][0] = base; pl["iparam"][1] = J
-                    self.emit_expr(sd)
+                    operands = [sd]
                     p.summary.append(f"plate NORM_GROUPED n={n} groups={J}")
         elif body.op == "LD_BERN" and data_i(body.args[0]) and _index_free(body.args[1]):
             pl.update(kind=PLATE_BERN_IID)
             pl["col"][0] = body.args[0].val[0]; pl["iparam"][2] = body.args[0].val[1]
-            self.emit_expr(body.args[1])
+            operands = [body.args[1]]
             p.summary.append(f"plate BERN_IID n={n}")
         elif body.op == "LD_POIS" and data_i(body.args[0]) and body.args[1].op == "EXP":
             lin = self._loglinear(body.args[1].args[0])
@@ -606,14 +636,15 @@ class Lowering:
                 p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
         p.plates.append(pl)
         if pl["kind"] != PLATE_GENERIC:
-            p.emit("PLATE", q)
+            modes, words = self._operands([self.prepared(o) for o in operands])
+            p.emit("PLATE", q, *words, modes=modes)
             return
         # generic: a bytecode loop, lp += body(i) in order
         p.emit("LOOP_BEGIN", q, 0)
         fix = len(p.code) - 1
         body_start = len(p.code)
         self.emit_expr(body)
-        p.emit("LOOP_END", body_start)
+        p.emit("LOOP_END", 0, body_start)
         p.code[fix] = len(p.code)
         p.summary.append(f"plate GENERIC n={n} body={body.op}")
 
@@ -664,8 +695,7 @@ class Lowering:
                 self._emit_plate(body, length)
                 i += length
                 continue
-            self.emit_expr(tm)
-            p.emit("ACC")
+            self.emit_expr(tm, acc=True)
             p.summary.append(f"term {tm.op}")
             i += 1
         p.emit("END")

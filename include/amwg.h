@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 2
+#define AMWG_ABI_VERSION 3
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -64,14 +64,30 @@ typedef struct {
 } amwg_column;
 
 /* ---- log_post as a program --------------------------------------------------------------
- * log_post(state, data) (mcmc.js:958-960) arrives as a postfix program over an fp64 stack, one
- * int32 word per instruction: (operand << 8) | opcode, plus one extra word where noted.
- * The accumulator `lp` starts at 0 and receives terms strictly in program order, so the sum is
- * formed in the same order as the JS `log_post += ...` statements.
- * Every arithmetic op is a single IEEE-754 fp64 operation (no FMA contraction); LOG/EXP are the
- * fdlibm algorithms V8's Math.log/Math.exp port; LD_* follow distributions.js operation by
- * operation (cited per opcode in csrc/amwg_ld.cuh).
+ * log_post(state, data) (mcmc.js:958-960) arrives as a postfix program over an fp64 stack.
+ * Instruction word (int32):
+ *     bits  0-7   opcode
+ *     bits  8-9   mode of operand A     0 = popped from the stack, 1 = consts[next word], 2 = state component [next word]
+ *     bits 10-11  mode of operand B     (operands are named in source order: op(A, B, C, D))
+ *     bits 12-13  mode of operand C
+ *     bits 14-15  mode of operand D
+ *     bit  16     ACC flag: the result is added to lp (lp = lp + result) instead of being pushed
+ *     bits 17-31  immediate `a` (const index, component, column, plate id ...)
+ * Inline operand words follow the instruction word in consumption order: last operand first (D, C, B, A), which is
+ * also the order stack operands are popped.  Further extra words are noted per opcode.
+ * The accumulator `lp` starts at 0 and receives terms strictly in program order, so the sum is formed in the same
+ * order as the JS `log_post += ...` statements.  Every arithmetic op is a single IEEE-754 fp64 operation (no FMA
+ * contraction); LOG/EXP are the fdlibm algorithms V8's Math.log/Math.exp port; LD_* follow distributions.js operation
+ * by operation (cited per opcode in csrc/amwg_ld.cuh).
  */
+#define AMWG_MODE_STACK 0
+#define AMWG_MODE_CONST 1
+#define AMWG_MODE_COMP 2
+#define AMWG_WORD(op, mA, mB, mC, mD, acc, a) \
+  ((int32_t)((uint32_t)(op) | ((uint32_t)(mA) << 8) | ((uint32_t)(mB) << 10) | ((uint32_t)(mC) << 12) | ((uint32_t)(mD) << 14) | \
+             ((uint32_t)((acc) ? 1 : 0) << 16) | ((uint32_t)(a) << 17)))
+#define AMWG_MAX_IMMEDIATE 32767
+
 enum {
   AMWG_OP_END = 0,
   AMWG_OP_CONST,        /* push consts[operand]                                             */
@@ -92,8 +108,8 @@ enum {
   AMWG_OP_ACC,          /* lp = lp + pop                                                     */
   AMWG_OP_PLATE,        /* lp = plate[operand](lp, popped operands): a recognised O(N) likelihood sum */
   AMWG_OP_STORE,        /* derived[operand] = pop   (derived-quantity program only)          */
-  AMWG_OP_LOOP_BEGIN,   /* start of a GENERIC plate body: i = 0 (plate[operand].n points; skipped when n == 0) */
-  AMWG_OP_LOOP_END,     /* lp = lp + pop; if (++i < n) jump to word `operand` (first word of the body) */
+  AMWG_OP_LOOP_BEGIN,   /* start of a GENERIC plate body: i = 0 (plate[a].n points); next word: offset to continue at when n == 0 */
+  AMWG_OP_LOOP_END,     /* lp = lp + pop; if (++i < n) jump to the word offset in the next word (first word of the body) */
   AMWG_OP__COUNT
 };
 
@@ -103,10 +119,10 @@ enum {
  * (AMWG_OP_LOOP_BEGIN ... AMWG_OP_LOOP_END, body uses DATA_I / COMP_I), bit-faithful to the JS loop. */
 enum {
   AMWG_PLATE_GENERIC = 0,   /* bytecode loop: lp += body(i), i = 0..n-1, in order                                   */
-  AMWG_PLATE_NORM_IID,      /* pops sd, mean.  sum_i ld.norm(x_i, mean, sd), factorised:
+  AMWG_PLATE_NORM_IID,      /* operands A = mean, B = sd.  sum_i ld.norm(x_i, mean, sd), factorised:
                                N*(-0.5*log(2pi) - log(sd)) - sum_i (x_i-mean)^2 / (2*sd*sd)     (KS-level parity)   */
-  AMWG_PLATE_BERN_IID,      /* pops p.  sum_i ld.bern(y_i, p), sequential, bit-faithful                              */
-  AMWG_PLATE_NORM_GROUPED,  /* pops sd. sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group                      */
+  AMWG_PLATE_BERN_IID,      /* operand A = p.  sum_i ld.bern(y_i, p), sequential, bit-faithful                       */
+  AMWG_PLATE_NORM_GROUPED,  /* operand A = sd.  sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group              */
   AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k))                                          */
 };
 

@@ -32,61 +32,67 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
     def comp(c):
         return val if c == moved else float(state[c])
 
+    def nxt():
+        nonlocal pc
+        v = code[pc]; pc += 1
+        return v
+
+    def opnd(mode):
+        if mode == 0:
+            return stk.pop()
+        ix = nxt()
+        return consts[ix] if mode == 1 else comp(ix)
+
+    def div(x, y):
+        if y != 0: return x / y
+        if x == 0 or x != x: return math.nan
+        return math.copysign(math.inf, x) * math.copysign(1.0, y)
+
+    BIN = {"ADD": lambda x, y: x + y, "SUB": lambda x, y: x - y, "MUL": lambda x, y: x * y, "DIV": div,
+           "POW": lambda x, y: x * x if y == 2.0 else math.pow(x, y),
+           "LT": lambda x, y: float(x < y), "LE": lambda x, y: float(x <= y), "GT": lambda x, y: float(x > y),
+           "GE": lambda x, y: float(x >= y), "EQ": lambda x, y: float(x == y), "NE": lambda x, y: float(x != y),
+           "AND": lambda x, y: float(x != 0 and y != 0), "OR": lambda x, y: float(x != 0 or y != 0),
+           "LCHOOSE": lambda x, y: _ld(O, "lchoose", x, y), "LBETA": lambda x, y: _ld(O, "lbeta", x, y)}
+    UN = {"NEG": lambda x: -x, "LOG": lambda x: O.orc_log(x), "EXP": lambda x: O.orc_exp(x),
+          "SQRT": lambda x: math.sqrt(x) if x >= 0 else math.nan, "ABS": abs, "NOT": lambda x: float(x == 0),
+          "LGAMMA": lambda x: _ld(O, "lgamma", x), "LFACTORIAL": lambda x: _ld(O, "lfactorial", x)}
     while True:
-        w = code[pc]; pc += 1
-        op, a = INV[w & 0xff], w >> 8
+        w = nxt() & 0xffffffff
+        op = INV[w & 0xff]
+        mA, mB, mC, mD = (w >> 8) & 3, (w >> 10) & 3, (w >> 12) & 3, (w >> 14) & 3
+        acc, a = (w >> 16) & 1, w >> 17
+        r = None
         if op == "END":
             return stk[-1] if (want_top and stk) else lp
-        if op == "CONST": stk.append(consts[a])
-        elif op == "COMP": stk.append(comp(a))
-        elif op == "DATA": stk.append(float(cols[a][code[pc]])); pc += 1
-        elif op == "DATA_I": stk.append(float(cols[a][code[pc] + code[pc + 1] * li])); pc += 2
+        if op == "CONST": r = consts[a]
+        elif op == "COMP": r = comp(a)
+        elif op == "DATA": r = float(cols[a][nxt()])
+        elif op == "DATA_I":
+            off = nxt(); stride = nxt(); r = float(cols[a][off + stride * li])
         elif op == "COMP_I":
-            off, stride, base = code[pc:pc + 3]; pc += 3
-            stk.append(comp(base + int(cols[a][off + stride * li])))
-        elif op in ("ADD", "SUB", "MUL", "DIV", "POW", "LT", "LE", "GT", "GE", "EQ", "NE", "AND", "OR"):
-            y = stk.pop(); x = stk.pop()
-            if op == "ADD": r = x + y
-            elif op == "SUB": r = x - y
-            elif op == "MUL": r = x * y
-            elif op == "DIV":
-                r = (x / y) if y != 0 else (math.nan if (x == 0 or x != x) else math.copysign(math.inf, x) * math.copysign(1.0, y))
-            elif op == "POW": r = x * x if y == 2.0 else math.pow(x, y)
-            elif op == "LT": r = float(x < y)
-            elif op == "LE": r = float(x <= y)
-            elif op == "GT": r = float(x > y)
-            elif op == "GE": r = float(x >= y)
-            elif op == "EQ": r = float(x == y)
-            elif op == "NE": r = float(x != y)
-            elif op == "AND": r = float(x != 0 and y != 0)
-            else: r = float(x != 0 or y != 0)
-            stk.append(r)
-        elif op == "NEG": stk.append(-stk.pop())
-        elif op == "LOG": stk.append(O.orc_log(stk.pop()))
-        elif op == "EXP": stk.append(O.orc_exp(stk.pop()))
-        elif op == "SQRT":
-            x = stk.pop(); stk.append(math.sqrt(x) if x >= 0 else math.nan)
-        elif op == "ABS": stk.append(abs(stk.pop()))
-        elif op == "NOT": stk.append(float(stk.pop() == 0))
+            off = nxt(); stride = nxt(); base = nxt()
+            r = comp(base + int(cols[a][off + stride * li]))
+        elif op in BIN:
+            y = opnd(mB); x = opnd(mA); r = BIN[op](x, y)
+        elif op in UN:
+            r = UN[op](opnd(mA))
         elif op == "SELECT":
-            b = stk.pop(); t = stk.pop(); c = stk.pop(); stk.append(t if c != 0 else b)
-        elif op in ("LGAMMA", "LFACTORIAL"):
-            stk.append(_ld(O, op.lower(), stk.pop()))
-        elif op in ("LCHOOSE", "LBETA"):
-            y = stk.pop(); x = stk.pop(); stk.append(_ld(O, op.lower(), x, y))
+            z = opnd(mC); y = opnd(mB); x = opnd(mA); r = y if x != 0 else z
         elif op.startswith("LD_"):
             n = {"LD_BERN": 2, "LD_POIS": 2, "LD_EXP": 2, "LD_T": 4, "LD_HYPER": 4}.get(op, 3)
-            args = stk[-n:]; del stk[-n:]
-            stk.append(_ld(O, op[3:].lower(), *args))
+            args = [opnd(m) for m in (mA, mB, mC, mD)[:n][::-1]][::-1]
+            r = _ld(O, op[3:].lower(), *args)
         elif op == "ACC": lp = lp + stk.pop()
         elif op == "STORE": der[a] = stk.pop()
         elif op == "LOOP_BEGIN":
-            skip = code[pc]; pc += 1
+            skip = nxt()
             li, ln = 0, plates[a]["n"]
             if ln <= 0: pc = skip
         elif op == "LOOP_END":
+            body = nxt()
             lp = lp + stk.pop(); li += 1
-            if li < ln: pc = a
+            if li < ln: pc = body
             else: li = 0
         elif op == "PLATE":
             pl = plates[a]
@@ -94,16 +100,16 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
             x = np.asarray(cols[pl["col"][0]][off:off + n], dtype=np.float64)
             c0 = -0.5 * O.orc_log(2 * JS_PI)
             if pl["kind"] == PLATE_NORM_IID:
-                sd = stk.pop(); mean = stk.pop()
+                sd = opnd(mB); mean = opnd(mA)
                 S = float(np.sum((x - mean) ** 2))
                 lp = lp + (n * (c0 - O.orc_log(sd)) - S / (2 * sd * sd))
             elif pl["kind"] == PLATE_BERN_IID:
-                p = stk.pop()
+                p = opnd(mA)
                 l1 = O.orc_log(1.0 * p + (1 - 1.0) * (1 - p)); l0 = O.orc_log(0.0 * p + (1 - 0.0) * (1 - p))
                 for yi in x:
                     lp = lp + (l1 if yi == 1.0 else (l0 if yi == 0.0 else -math.inf))
             elif pl["kind"] == PLATE_NORM_GROUPED:
-                sd = stk.pop()
+                sd = opnd(mA)
                 start = cols[pl["col"][1]].astype(int); base, J = pl["iparam"][0], pl["iparam"][1]
                 S = 0.0
                 for j in range(J):
@@ -120,6 +126,9 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
                 raise AssertionError("generic plates are LOOP_BEGIN/LOOP_END")
         else:
             raise AssertionError(op)
+        if r is not None:
+            if acc: lp = lp + r
+            else: stk.append(r)
 
 
 def logpost(prog, consts, state, O, moved=-1, val=0.0):
