@@ -82,6 +82,7 @@ struct Ctx {                       // lives in shared memory
   const amwg_param* params;
   const double* col[kMaxColumns];  // generic pointers (shared or global)
   unsigned col_saddr[kMaxColumns]; // 32-bit shared-window address, 0 when the column is served from global/L2
+  double norm_c0;                  // -0.5 * Math.log(2 * Math.PI), evaluated once per CTA with the device's js_log
 };
 
 struct EvalState {
@@ -142,6 +143,7 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
       ctx.col[k] = in_smem ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
       ctx.col_saddr[k] = in_smem ? smem_u32(smem + m.col_smem_off[k]) : 0u;
     }
+    ctx.norm_c0 = -0.5 * js_log(2 * AMWG_JS_PI);
   }
   __syncthreads();
   mbar_wait(bar, 0);
@@ -174,9 +176,8 @@ __device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, unsig
   return (s0 + s1) + (s2 + s3);
 }
 
-__device__ __forceinline__ double norm_factorised(double n, double S, double sd) {
-  double c0 = -0.5 * js_log(2 * AMWG_JS_PI);
-  return n * (c0 - js_log(sd)) - S / (2 * sd * sd);
+__device__ __forceinline__ double norm_factorised(const Ctx& ctx, double n, double S, double sd) {
+  return n * (ctx.norm_c0 - js_log(sd)) - S / (2 * sd * sd);
 }
 
 __device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean, double sd) {
@@ -184,7 +185,7 @@ __device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean
   int c = pl.col[0], off = pl.iparam[2];
   unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)off : 0u;
   double S = sum_sq_dev(ctx.col[c] + off, sa, pl.n, mean);
-  return norm_factorised((double)pl.n, S, sd);
+  return norm_factorised(ctx, (double)pl.n, S, sd);
 }
 
 // sum_i ld.bern(y_i, p): sequential, bit-faithful to distributions.js:228-230 (x*prob + (1-x)*(1-prob) is exact for x in {0,1}).
@@ -212,7 +213,7 @@ __device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const E
     unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)a : 0u;
     S = S + sum_sq_dev(ctx.col[c] + a, sa, b - a, es.comp(base + j));
   }
-  return norm_factorised((double)pl.n, S, sd);
+  return norm_factorised(ctx, (double)pl.n, S, sd);
 }
 
 // sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop), using log(exp(eta)) -> eta
@@ -243,6 +244,53 @@ __device__ __noinline__ double plate_pois_loglin(const Ctx& ctx, int q, const Ev
 __device__ __forceinline__ unsigned lds_u32(unsigned saddr) { unsigned v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr)); return v; }
 __device__ __forceinline__ double lds_f64(unsigned saddr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr)); return v; }
 
+// Rare opcodes (the ld.* that are not expanded into primitives by the host, lgamma & co, general pow) live out of line so
+// that the interpreter's hot loop stays a few hundred instructions.
+__device__ __noinline__ double cold_op(int op, double x, double y, double z, double t) {
+  switch (op) {
+    case AMWG_OP_POW: return pow(x, y);
+    case AMWG_OP_LGAMMA: return ld_lgamma(x);
+    case AMWG_OP_LFACTORIAL: return ld_lfactorial(x);
+    case AMWG_OP_LCHOOSE: return ld_lchoose(x, y);
+    case AMWG_OP_LBETA: return ld_lbeta(x, y);
+    case AMWG_OP_LD_NORM: return ld_norm(x, y, z);
+    case AMWG_OP_LD_UNIF: return ld_unif(x, y, z);
+    case AMWG_OP_LD_BETA: return ld_beta(x, y, z);
+    case AMWG_OP_LD_BERN: return ld_bern(x, y);
+    case AMWG_OP_LD_POIS: return ld_pois(x, y);
+    case AMWG_OP_LD_CAUCHY: return ld_cauchy(x, y, z);
+    case AMWG_OP_LD_LAPLACE: return ld_laplace(x, y, z);
+    case AMWG_OP_LD_GAMMA: return ld_gamma(x, y, z);
+    case AMWG_OP_LD_INVGAMMA: return ld_invgamma(x, y, z);
+    case AMWG_OP_LD_LNORM: return ld_lnorm(x, y, z);
+    case AMWG_OP_LD_PARETO: return ld_pareto(x, y, z);
+    case AMWG_OP_LD_T: return ld_t(x, y, z, t);
+    case AMWG_OP_LD_WEIBULL: return ld_weibull(x, y, z);
+    case AMWG_OP_LD_LOGIS: return ld_logis(x, y, z);
+    case AMWG_OP_LD_EXP: return ld_exp(x, y);
+    case AMWG_OP_LD_BINOM: return ld_binom(x, y, z);
+    case AMWG_OP_LD_NBINOM: return ld_nbinom(x, y, z);
+    case AMWG_OP_LD_HYPER: return ld_hyper(x, y, z, t);
+    default: return CUDART_NAN;
+  }
+}
+
+// number of value operands (A..D) of each opcode
+__device__ __forceinline__ int op_arity(int op) {
+  if (op <= AMWG_OP_COMP_I) return 0;
+  if (op <= AMWG_OP_DIV) return 2;                    // ADD SUB MUL DIV
+  if (op <= AMWG_OP_ABS) return 1;                    // NEG LOG EXP SQRT ABS
+  if (op <= AMWG_OP_OR) return 2;                     // POW LT LE GT GE EQ NE AND OR
+  if (op == AMWG_OP_NOT) return 1;
+  if (op == AMWG_OP_SELECT) return 3;
+  if (op <= AMWG_OP_LFACTORIAL) return 1;             // LGAMMA LFACTORIAL
+  if (op <= AMWG_OP_LBETA) return 2;                  // LCHOOSE LBETA
+  if (op == AMWG_OP_LD_BERN || op == AMWG_OP_LD_POIS || op == AMWG_OP_LD_EXP) return 2;
+  if (op == AMWG_OP_LD_T || op == AMWG_OP_LD_HYPER) return 4;
+  if (op <= AMWG_OP_LD_HYPER) return 3;
+  return 0;                                           // ACC PLATE STORE LOOP_* END fetch their own
+}
+
 __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalState& es, int pc,
                                            double* der, bool want_top) {
   double stk[kStack];
@@ -257,15 +305,18 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
     if ((mode) == AMWG_MODE_STACK) { AMWG_POP(dst); }                                      \
     else { int _ix = AMWG_NEXT(); dst = ((mode) == AMWG_MODE_CONST) ? lds_f64(consts_sa + 8u * (unsigned)_ix) : es.comp(_ix); } \
   } while (0)
-#define AMWG_UN(expr) { double x; AMWG_OPND(x, mA); r = (expr); break; }
-#define AMWG_BIN(expr) { double x, y; AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
-#define AMWG_TER(expr) { double x, y, z; AMWG_OPND(z, mC); AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
-#define AMWG_QUA(expr) { double x, y, z, t; AMWG_OPND(t, mD); AMWG_OPND(z, mC); AMWG_OPND(y, mB); AMWG_OPND(x, mA); r = (expr); break; }
   for (;;) {
     const unsigned w = (unsigned)AMWG_NEXT();
-    const int op = w & 0xff, mA = (w >> 8) & 3, mB = (w >> 10) & 3, mC = (w >> 12) & 3, mD = (w >> 14) & 3;
+    const int op = w & 0xff;
     const bool acc = (w >> 16) & 1;
     const int a = (int)(w >> 17);
+    // operands, last one first (the order inline words are laid out and stack operands are popped)
+    double x = 0.0, y = 0.0, z = 0.0, t = 0.0;
+    const int nops = op_arity(op);
+    if (nops >= 4) AMWG_OPND(t, (w >> 14) & 3);
+    if (nops >= 3) AMWG_OPND(z, (w >> 12) & 3);
+    if (nops >= 2) AMWG_OPND(y, (w >> 10) & 3);
+    if (nops >= 1) AMWG_OPND(x, (w >> 8) & 3);
     double r = 0.0;
     bool has_r = true;
     switch (op) {
@@ -278,57 +329,41 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
         r = es.comp(base + (int)ctx.col[a][off + stride * loop_i]);
         break;
       }
-      case AMWG_OP_ADD: AMWG_BIN(x + y)
-      case AMWG_OP_SUB: AMWG_BIN(x - y)
-      case AMWG_OP_MUL: AMWG_BIN(x * y)
-      case AMWG_OP_DIV: AMWG_BIN(x / y)
-      case AMWG_OP_NEG: AMWG_UN(-x)
-      case AMWG_OP_LOG: AMWG_UN(js_log(x))
-      case AMWG_OP_EXP: AMWG_UN(js_exp(x))
-      case AMWG_OP_SQRT: AMWG_UN(sqrt(x))
-      case AMWG_OP_ABS: AMWG_UN(fabs(x))
-      case AMWG_OP_POW: AMWG_BIN(js_pow(x, y))
-      case AMWG_OP_LT: AMWG_BIN(x < y ? 1.0 : 0.0)
-      case AMWG_OP_LE: AMWG_BIN(x <= y ? 1.0 : 0.0)
-      case AMWG_OP_GT: AMWG_BIN(x > y ? 1.0 : 0.0)
-      case AMWG_OP_GE: AMWG_BIN(x >= y ? 1.0 : 0.0)
-      case AMWG_OP_EQ: AMWG_BIN(x == y ? 1.0 : 0.0)
-      case AMWG_OP_NE: AMWG_BIN(x != y ? 1.0 : 0.0)
-      case AMWG_OP_AND: AMWG_BIN((x != 0.0 && y != 0.0) ? 1.0 : 0.0)
-      case AMWG_OP_OR: AMWG_BIN((x != 0.0 || y != 0.0) ? 1.0 : 0.0)
-      case AMWG_OP_NOT: AMWG_UN(x != 0.0 ? 0.0 : 1.0)
-      case AMWG_OP_SELECT: AMWG_TER(x != 0.0 ? y : z)
-      case AMWG_OP_LGAMMA: AMWG_UN(ld_lgamma(x))
-      case AMWG_OP_LFACTORIAL: AMWG_UN(ld_lfactorial(x))
-      case AMWG_OP_LCHOOSE: AMWG_BIN(ld_lchoose(x, y))
-      case AMWG_OP_LBETA: AMWG_BIN(ld_lbeta(x, y))
-      case AMWG_OP_LD_NORM: AMWG_TER(ld_norm(x, y, z))
-      case AMWG_OP_LD_UNIF: AMWG_TER(ld_unif(x, y, z))
-      case AMWG_OP_LD_BETA: AMWG_TER(ld_beta(x, y, z))
-      case AMWG_OP_LD_BERN: AMWG_BIN(ld_bern(x, y))
-      case AMWG_OP_LD_POIS: AMWG_BIN(ld_pois(x, y))
-      case AMWG_OP_LD_CAUCHY: AMWG_TER(ld_cauchy(x, y, z))
-      case AMWG_OP_LD_LAPLACE: AMWG_TER(ld_laplace(x, y, z))
-      case AMWG_OP_LD_GAMMA: AMWG_TER(ld_gamma(x, y, z))
-      case AMWG_OP_LD_INVGAMMA: AMWG_TER(ld_invgamma(x, y, z))
-      case AMWG_OP_LD_LNORM: AMWG_TER(ld_lnorm(x, y, z))
-      case AMWG_OP_LD_PARETO: AMWG_TER(ld_pareto(x, y, z))
-      case AMWG_OP_LD_T: AMWG_QUA(ld_t(x, y, z, t))
-      case AMWG_OP_LD_WEIBULL: AMWG_TER(ld_weibull(x, y, z))
-      case AMWG_OP_LD_LOGIS: AMWG_TER(ld_logis(x, y, z))
-      case AMWG_OP_LD_EXP: AMWG_BIN(ld_exp(x, y))
-      case AMWG_OP_LD_BINOM: AMWG_TER(ld_binom(x, y, z))
-      case AMWG_OP_LD_NBINOM: AMWG_TER(ld_nbinom(x, y, z))
-      case AMWG_OP_LD_HYPER: AMWG_QUA(ld_hyper(x, y, z, t))
-      case AMWG_OP_ACC: { double x; AMWG_POP(x); lp = lp + x; has_r = false; break; }
+      case AMWG_OP_ADD: r = x + y; break;
+      case AMWG_OP_SUB: r = x - y; break;
+      case AMWG_OP_MUL: r = x * y; break;
+      case AMWG_OP_DIV: r = x / y; break;
+      case AMWG_OP_NEG: r = -x; break;
+      case AMWG_OP_LOG: r = js_log(x); break;
+      case AMWG_OP_EXP: r = js_exp(x); break;
+      case AMWG_OP_SQRT: r = sqrt(x); break;
+      case AMWG_OP_ABS: r = fabs(x); break;
+      case AMWG_OP_POW: r = (y == 2.0) ? x * x : cold_op(op, x, y, z, t); break;
+      case AMWG_OP_LT: r = x < y ? 1.0 : 0.0; break;
+      case AMWG_OP_LE: r = x <= y ? 1.0 : 0.0; break;
+      case AMWG_OP_GT: r = x > y ? 1.0 : 0.0; break;
+      case AMWG_OP_GE: r = x >= y ? 1.0 : 0.0; break;
+      case AMWG_OP_EQ: r = x == y ? 1.0 : 0.0; break;
+      case AMWG_OP_NE: r = x != y ? 1.0 : 0.0; break;
+      case AMWG_OP_AND: r = (x != 0.0 && y != 0.0) ? 1.0 : 0.0; break;
+      case AMWG_OP_OR: r = (x != 0.0 || y != 0.0) ? 1.0 : 0.0; break;
+      case AMWG_OP_NOT: r = x != 0.0 ? 0.0 : 1.0; break;
+      case AMWG_OP_SELECT: r = x != 0.0 ? y : z; break;
+      case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
       case AMWG_OP_PLATE: {
         has_r = false;
-        switch (ctx.plates[a].kind) {
-          case AMWG_PLATE_NORM_IID: { double mean, sd; AMWG_OPND(sd, mB); AMWG_OPND(mean, mA); lp = lp + plate_norm_iid(ctx, a, mean, sd); break; }
-          case AMWG_PLATE_BERN_IID: { double p; AMWG_OPND(p, mA); lp = plate_bern_iid(ctx, a, p, lp); break; }
-          case AMWG_PLATE_NORM_GROUPED: { double sd; AMWG_OPND(sd, mA); lp = lp + plate_norm_grouped(ctx, a, es, sd); break; }
-          case AMWG_PLATE_POIS_LOGLIN: lp = lp + plate_pois_loglin(ctx, a, es); break;
-          default: break;
+        const int kind = ctx.plates[a].kind;
+        if (kind == AMWG_PLATE_NORM_IID) {
+          double mean, sd; AMWG_OPND(sd, (w >> 10) & 3); AMWG_OPND(mean, (w >> 8) & 3);
+          lp = lp + plate_norm_iid(ctx, a, mean, sd);
+        } else if (kind == AMWG_PLATE_BERN_IID) {
+          double p; AMWG_OPND(p, (w >> 8) & 3);
+          lp = plate_bern_iid(ctx, a, p, lp);
+        } else if (kind == AMWG_PLATE_NORM_GROUPED) {
+          double sd; AMWG_OPND(sd, (w >> 8) & 3);
+          lp = lp + plate_norm_grouped(ctx, a, es, sd);
+        } else if (kind == AMWG_PLATE_POIS_LOGLIN) {
+          lp = lp + plate_pois_loglin(ctx, a, es);
         }
         break;
       }
@@ -341,15 +376,15 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
       }
       case AMWG_OP_LOOP_END: {
         int body = AMWG_NEXT();
-        double x; AMWG_POP(x);
-        lp = lp + x;
+        double v; AMWG_POP(v);
+        lp = lp + v;
         if (++loop_i < loop_n) pc = body; else loop_i = 0;
         has_r = false;
         break;
       }
-      case AMWG_OP_STORE: { double x; AMWG_POP(x); der[a] = x; has_r = false; break; }
-      default:   // AMWG_OP_END
-        return (want_top && sp > 0) ? tos : lp;
+      case AMWG_OP_STORE: { double v; AMWG_POP(v); der[a] = v; has_r = false; break; }
+      case AMWG_OP_END: return (want_top && sp > 0) ? tos : lp;
+      default: r = cold_op(op, x, y, z, t); break;
     }
     if (has_r) {
       if (acc) lp = lp + r;
@@ -359,10 +394,6 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
 #undef AMWG_NEXT
 #undef AMWG_POP
 #undef AMWG_OPND
-#undef AMWG_UN
-#undef AMWG_BIN
-#undef AMWG_TER
-#undef AMWG_QUA
 }
 
 __device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
