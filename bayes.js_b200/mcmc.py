@@ -5,8 +5,8 @@
 
 Same names, argument meaning and error strings as the reference; the stepping itself happens in
 libamwg_b200.so (CUDA, sm_100a) for ``options["chains"]`` independent chains at once.  The host
-language is Python because no JavaScript engine exists in this image; js/ holds the equivalent
-CommonJS shim + N-API addon source a Node host would use.
+language is Python because no JavaScript engine exists in this image; INTEGRATION.md shows the N-API
+binding a Node host would put under the same `mcmc` / `ld` module names.
 
 New, non-reference options (the many-chain setting needs them): ``chains`` (default 1: output is
 shaped exactly like the reference's), ``seed``, ``device``, ``distributed``.
