@@ -43,14 +43,15 @@ def all_gather_chain_axis(local, counts):
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size()
-    if len(set(counts)) == 1:
-        # equal blocks: one all_gather_into_tensor over a [ws, rows, entries, c] buffer
-        out = torch.empty((ws,) + tuple(local.shape), dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous())
-        return torch.cat(list(out.unbind(0)), dim=-1)
-    parts = [torch.empty(tuple(local.shape[:-1]) + (c,), dtype=local.dtype, device=local.device) for c in counts]
-    dist.all_gather(parts, local.contiguous())
-    return torch.cat(parts, dim=-1)
+    cmax = max(counts)
+    if local.shape[-1] < cmax:                         # ragged shards: pad to the largest block (collectives want equal sizes)
+        pad = torch.zeros(tuple(local.shape[:-1]) + (cmax - local.shape[-1],), dtype=local.dtype, device=local.device)
+        local = torch.cat([local, pad], dim=-1)
+    shp = tuple(local.shape)
+    out = torch.empty((ws * shp[0],) + shp[1:], dtype=local.dtype, device=local.device)          # rank blocks concatenated on dim 0
+    dist.all_gather_into_tensor(out, local.contiguous())
+    blocks = out.view((ws,) + shp).unbind(0)
+    return torch.cat([b[..., :c] for b, c in zip(blocks, counts)], dim=-1)
 
 
 def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) -> np.ndarray:
