@@ -9,7 +9,8 @@ language is Python because no JavaScript engine exists in this image; INTEGRATIO
 binding a Node host would put under the same `mcmc` / `ld` module names.
 
 New, non-reference options (the many-chain setting needs them): ``chains`` (default 1: output is
-shaped exactly like the reference's), ``seed``, ``device``, ``distributed``.
+shaped exactly like the reference's), ``seed``, ``device``, ``distributed``, ``first_chain`` (global id of
+the first chain, default 0), ``faithful`` (no factorised likelihood plates: bit-faithful, slower).
 """
 from __future__ import annotations
 
@@ -311,6 +312,7 @@ class AmwgSampler(Sampler):
         self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self.device = int(get_option("device", options, _default_device()))
         self.distributed = bool(get_option("distributed", options, False))
+        self.faithful = bool(get_option("faithful", options, False))      # no factorised plates: bit-faithful sums, slower
 
         # flat component layout: Object.keys(params) order, row-major inside a parameter
         self._offsets: Dict[str, int] = {}
@@ -321,10 +323,10 @@ class AmwgSampler(Sampler):
         self.n_comp = n_comp
 
         resolved = resolve_stepper_options(self.params, options)
-        self._program, self._derived_names = trace(self._user_log_post, self.params, self._offsets, n_comp, self.data)
+        self._program, self._derived_names = trace(self._user_log_post, self.params, self._offsets, n_comp, self.data, self.faithful)
 
         # shard the chains when running one process per GPU (torch.distributed, see parallel.py)
-        self.first_chain, self.local_chains = 0, self.n_chains
+        self.first_chain, self.local_chains = int(get_option("first_chain", options, 0)), self.n_chains
         if self.distributed:
             from .parallel import shard_chains
             self.first_chain, self.local_chains = shard_chains(self.n_chains)

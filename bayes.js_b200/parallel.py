@@ -38,28 +38,36 @@ def shard_chains(n_chains: int) -> Tuple[int, int]:
 
 
 def all_gather_chain_axis(local, counts):
-    """All-gather tensors that differ only in their last (chain) axis. `counts[r]` = chains of rank r.
-    Works for CUDA tensors over NCCL and CPU tensors over gloo."""
+    """All-gather `local[rows, entries, c_rank]` over its last (chain) axis -> `[rows, entries, sum(counts)]`, chains in
+    global order. One collective per (row, entry) slab, written straight into its final place (the kernel's layout keeps the
+    chain axis fastest, so a single dim-0 all-gather would interleave ranks). CUDA tensors over NCCL, CPU tensors over gloo."""
     import torch
     import torch.distributed as dist
     ws = dist.get_world_size()
+    rows, entries = local.shape[0], local.shape[1]
     cmax = max(counts)
-    if local.shape[-1] < cmax:                         # ragged shards: pad to the largest block (collectives want equal sizes)
-        pad = torch.zeros(tuple(local.shape[:-1]) + (cmax - local.shape[-1],), dtype=local.dtype, device=local.device)
+    ragged = len(set(counts)) > 1
+    if ragged and local.shape[-1] < cmax:              # pad to the largest block (collectives want equal sizes)
+        pad = torch.zeros((rows, entries, cmax - local.shape[-1]), dtype=local.dtype, device=local.device)
         local = torch.cat([local, pad], dim=-1)
-    shp = tuple(local.shape)
-    out = torch.empty((ws * shp[0],) + shp[1:], dtype=local.dtype, device=local.device)          # rank blocks concatenated on dim 0
-    dist.all_gather_into_tensor(out, local.contiguous())
-    blocks = out.view((ws,) + shp).unbind(0)
-    return torch.cat([b[..., :c] for b, c in zip(blocks, counts)], dim=-1)
+    local = local.contiguous()
+    out = torch.empty((rows, entries, ws * cmax), dtype=local.dtype, device=local.device)
+    for r in range(rows):
+        for e in range(entries):
+            dist.all_gather_into_tensor(out[r, e], local[r, e])
+    if not ragged:
+        return out
+    keep = torch.cat([torch.arange(k * cmax, k * cmax + c, device=local.device) for k, c in enumerate(counts)])
+    return out.index_select(-1, keep)
 
 
 def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) -> np.ndarray:
-    """sample() on this rank's shard into a device buffer, all-gather over the chain axis, then D2H.
-    Returns [rows, n_entries, total_chains] on every rank."""
+    """sample() on this rank's shard into a device buffer, all-gather over the chain axis (NCCL over NVLink), then one
+    D2H into a pinned host buffer. Returns [rows, n_entries, total_chains] on every rank."""
     import torch
     import torch.distributed as dist
     from . import _ffi
+    from .mcmc import _pinned_empty
     from .tracer import JsThrow
     if not (dist.is_available() and dist.is_initialized()):
         raise JsThrow("options.distributed needs an initialised torch.distributed process group")
@@ -73,4 +81,7 @@ def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) ->
     ws = dist.get_world_size()
     counts = [shard_bounds(sampler.n_chains, r, ws)[1] for r in range(ws)]
     full = all_gather_chain_axis(local, counts)
-    return full.cpu().numpy()
+    host = _pinned_empty(tuple(full.shape))
+    torch.from_numpy(host).copy_(full, non_blocking=True)
+    torch.cuda.synchronize(dev)
+    return host

@@ -500,9 +500,10 @@ def _index_free(node: Sym) -> bool:
 
 
 class Lowering:
-    def __init__(self, tracer: Tracer, n_comp: int):
+    def __init__(self, tracer: Tracer, n_comp: int, faithful: bool = False):
         self.t = tracer
         self.n_comp = n_comp
+        self.faithful = faithful                 # True: no factorised plates -- every likelihood loop is added term by term like the JS loop
         self.prog = Program()
         self.prog.columns = tracer.columns       # shared list: synthesized columns are appended
         self._fold_memo: Dict[tuple, int] = {}
@@ -601,7 +602,9 @@ class Lowering:
 
         q = len(p.plates)
         operands: List[Sym] = []
-        if body.op == "LD_NORM" and data_i(body.args[0]) and _index_free(body.args[2]):
+        if self.faithful and body.op in ("LD_NORM", "LD_POIS"):
+            pass                                                  # bytecode loop below: bit-faithful to the reference's arithmetic
+        elif body.op == "LD_NORM" and data_i(body.args[0]) and _index_free(body.args[2]):
             x, mean, sd = body.args
             if _index_free(mean):
                 pl.update(kind=PLATE_NORM_IID)
@@ -811,7 +814,7 @@ def _lfactorial_host(y: float) -> float:
     return math.log(2.5066282746310005 * ser / xx) - tmp
 
 
-def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: int, data) -> Tuple[Program, List[str]]:
+def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: int, data, faithful: bool = False) -> Tuple[Program, List[str]]:
     """Run `log_post` once symbolically; return the lowered program and the derived-quantity names."""
     tr = Tracer()
     state = tr.make_state(params, offsets)
@@ -828,7 +831,7 @@ def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: in
     for k, v in derived.items():
         if not isinstance(v, (Sym, numbers.Real)):
             raise JsThrow(f"derived quantity {k} must be a number")
-    prog = Lowering(tr, n_comp).lower(result, derived)
+    prog = Lowering(tr, n_comp, faithful).lower(result, derived)
     return prog, list(derived.keys())
 
 

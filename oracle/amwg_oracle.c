@@ -8,14 +8,15 @@
  * The product (bayes.js_b200/) never includes, links or calls anything in oracle/.
  *
  * Pinning status (see DESIGN.md "Oracle"):
- *   - pinned against the reference's only deterministic fixtures (complete_params goldens,
- *     tests/test_data.js:20-35,50-74) and the closed-form known answers of SURVEY.md 8(c);
- *   - pinned draw-for-draw against the UNMODIFIED /root/reference/mcmc.js + distributions.js
- *     executed by oracle/minijs (an ES5 interpreter written for this purpose, because no JS
- *     engine exists in the image) with Math.random replaced by the Philox stream below;
- *     vectors are committed under tests/golden/ with the script that made them;
- *   - exact equality with V8's Math.log/Math.exp is "parity unpinned": V8 is not runnable
- *     here; orc_log/orc_exp restate the fdlibm algorithms V8's ieee754::log/exp are ports of.
+ *   - pinned DRAW FOR DRAW against the UNMODIFIED /root/reference/mcmc.js + distributions.js + tests/test_data.js, executed
+ *     by oracle/minijs (an ES5 interpreter written for this purpose, because no JS engine exists in the image) with
+ *     Math.random replaced by the Philox stream below: 28 sampler scenarios covering every stepper kind, options, thin,
+ *     monitor and adaptation toggles, plus every ld.* function, complete_params, param_init_fixed and the helpers.
+ *     Vectors: tests/golden/reference_js.json; generator: oracle/minijs/make_golden.py; check: tests/test_golden.py;
+ *   - pinned against the reference's only deterministic fixtures (complete_params goldens, tests/test_data.js:20-35,50-74)
+ *     and the closed-form known answers of SURVEY.md 8(c) (tests/test_oracle.py);
+ *   - exact equality with V8's own Math.log/Math.exp/Math.pow is "parity unpinned": V8 is not runnable here;
+ *     orc_log/orc_exp restate the fdlibm algorithms V8's ieee754::log/exp are ports of (<= 1 ulp from glibc, checked).
  *
  * Every function cites the reference lines it follows (paths under /root/reference/).
  * Build: oracle/Makefile  (gcc -O2 -ffp-contract=off -fno-fast-math).

@@ -254,6 +254,10 @@ class OracleSampler:
     def burn(self, n: int):
         lib().orc_burn(self.h, n)
 
+    def set_thin(self, k: int):
+        lib().orc_thin(self.h, k)
+        self.thin = k
+
     def step(self):
         lib().orc_step(self.h)
 

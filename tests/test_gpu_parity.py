@@ -33,10 +33,12 @@ def test_primitives_bit_exact(gpu_pkg, orc):
     assert np.array_equal(out, np.array([O.orc_js_round(v) for v in x]))
     n = 4097
     out = np.empty(n)
-    gpu_pkg._ffi.check(L.amwg_primitive_eval(2, np.zeros(n).ctypes.data, n, 12345, 77, out.ctypes.data, 0))
+    dummy = np.zeros(n)
+    gpu_pkg._ffi.check(L.amwg_primitive_eval(2, dummy.ctypes.data, n, 12345, 77, out.ctypes.data, 0))
     assert np.array_equal(out, np.array([O.orc_stream_uniform(12345, 77, i) for i in range(n)]))
     out = np.empty(5000)
-    gpu_pkg._ffi.check(L.amwg_primitive_eval(3, np.array([10.0, 5.0] + [0.0] * 4998).ctypes.data, 5000, 9, 3, out.ctypes.data, 0))
+    mean_sd = np.array([10.0, 5.0] + [0.0] * 4998)            # keep alive across the call
+    gpu_pkg._ffi.check(L.amwg_primitive_eval(3, mean_sd.ctypes.data, 5000, 9, 3, out.ctypes.data, 0))
     import ctypes
     pos = ctypes.c_uint64(0)
     ref = np.array([O.orc_rnorm(9, 3, ctypes.byref(pos), 10.0, 5.0) for _ in range(5000)])
