@@ -1,0 +1,145 @@
+"""GPU tests of the BASELINE configs: config 2 at full size against the exact posterior (KS < 0.01), configs 4 and 5 at
+oracle-sized inputs (bit-exact in faithful mode, statistical with the factorised plates), properties at larger sizes."""
+import numpy as np
+import pytest
+
+import models
+from conftest import config2_data
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_posterior_cdfs(x):
+    """Exact marginal CDFs of (mu, sigma) for the README model (N(0,100) x U(0,100) priors), by grid integration."""
+    n, xbar = x.size, x.mean()
+    S = float(np.sum((x - xbar) ** 2))
+    s = np.sqrt(S / (n - 1))
+    mu = np.linspace(xbar - 9 * s / np.sqrt(n), xbar + 9 * s / np.sqrt(n), 1201)
+    sg = np.linspace(s * 0.72, s * 1.38, 1201)
+    M, SG = np.meshgrid(mu, sg, indexing="ij")
+    lp = -0.5 * (M / 100.0) ** 2 - n * np.log(SG) - (S + n * (xbar - M) ** 2) / (2 * SG ** 2)
+    p = np.exp(lp - lp.max())
+    pm, ps = p.sum(axis=1), p.sum(axis=0)
+    return (mu, np.cumsum(pm) / pm.sum()), (sg, np.cumsum(ps) / ps.sum())
+
+
+def _ks_against_cdf(samples, grid, cdf):
+    xs = np.sort(samples)
+    F = np.interp(xs, grid, cdf, left=0.0, right=1.0)
+    n = xs.size
+    return max(np.max(np.arange(1, n + 1) / n - F), np.max(F - np.arange(0, n) / n))
+
+
+def test_config2_full_size_ks_against_exact_posterior(gpu_pkg):
+    """BASELINE config 2: N=1024, 2^20 chains. One draw per chain after burn-in, pooled: KS < 0.01 on both marginals
+    (north_star's tolerance) against the exact posterior; the reference's own tests compare against JAGS at p > 0.01."""
+    x = config2_data()
+    s = gpu_pkg.mcmc.AmwgSampler(models.PARAMS_NORM, models.norm_post_readme(gpu_pkg.ld), x.tolist(), {"chains": 1 << 20, "seed": 0})
+    assert s.program_summary()[-1] == "plate NORM_IID n=1024"
+    s.burn(3000)
+    d = s.sample(1)
+    (gm, cm), (gs, cs) = _grid_posterior_cdfs(x)
+    ks_mu = _ks_against_cdf(d["mu"].reshape(-1), gm, cm)
+    ks_sg = _ks_against_cdf(d["sigma"].reshape(-1), gs, cs)
+    assert ks_mu < 0.01 and ks_sg < 0.01, (ks_mu, ks_sg)
+    # every chain is in the support and has adapted its proposal scale
+    assert np.all(d["sigma"] > 0) and np.all(np.isfinite(d["mu"]))
+    info = s.info()["steppers"][0]
+    assert info["mu"]["batch_count"] == 60 and np.all(np.abs(info["mu"]["prop_log_scale"] - np.log(0.14 * 2.4)) < 1.5)
+
+
+def _hier(J, per, seed):
+    rng = np.random.default_rng(seed)
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(100, 20, J)[g] + rng.normal(0, 5, J * per)
+    params = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
+    return y, g, params
+
+
+def hier_post(ld, J):
+    def f(state, d):                               # BASELINE config 4
+        lp = 0
+        for j in range(J):
+            lp += ld.norm(state.mu[j], 0, 100)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]], state.sigma)
+        return lp
+    return f
+
+
+def test_config4_hierarchical_normal(gpu_pkg, orc):
+    J, per = 8, 32
+    y, g, params = _hier(J, per, 64)
+    data = {"y": y.tolist(), "g": g.tolist()}
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    # faithful: every draw equals the oracle (random top-level order over mu[0..J), D = J+1 components)
+    s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 64, "seed": 5, "faithful": True})
+    s.burn(60)
+    got = s.sample(40)
+    ref = orc.run_model("hier_norm", {"y": y, "g": g}, params, chains=64, seed=5, burn=60, sample=40)
+    assert got["mu"].shape == (40, 64, J)
+    assert np.array_equal(got["mu"], ref["mu"]) and np.array_equal(got["sigma"], ref["sigma"])
+    # fast path (one factorised plate per group): same posterior
+    s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 4096, "seed": 6})
+    assert s.program_summary()[-J:] == [f"plate NORM_IID n={per}"] * J
+    s.burn(1500)
+    fast = s.sample(1)
+    ref = orc.run_model("hier_norm", {"y": y, "g": g}, params, chains=1024, seed=6, burn=1500, sample=1)
+    from scipy import stats
+    for j in (0, J - 1):
+        assert stats.ks_2samp(fast["mu"][0, :, j], ref["mu"][0, :, j]).statistic < 0.06
+        assert abs(fast["mu"][0, :, j].mean() - y[g == j].mean()) < 0.2
+    assert stats.ks_2samp(fast["sigma"].reshape(-1), ref["sigma"].reshape(-1)).statistic < 0.06
+
+
+def poisreg_post(ld, mcmc, K):
+    def f(state, d):                               # BASELINE config 5
+        lp = 0
+        for k in range(K):
+            lp += ld.norm(state.beta[k], 0, 10)
+        for i in mcmc.points(len(d.y)):
+            eta = 0
+            for k in range(K):
+                eta += d.X[i][k] * state.beta[k]
+            lp += ld.pois(d.y[i], mcmc.Math.exp(eta))
+        return lp
+    return f
+
+
+def test_config5_poisson_regression(gpu_pkg, orc):
+    K, n = 4, 300
+    rng = np.random.default_rng(8)
+    X = np.column_stack([np.ones(n), rng.normal(0, 0.5, (n, K - 1))])
+    beta_true = rng.normal(0, 0.3, K)
+    yy = rng.poisson(np.exp(X @ beta_true)).astype(float)
+    params = {"beta": {"type": "real", "dim": [K]}}
+    data = {"y": yy.tolist(), "X": X.tolist()}
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    s = mcmc.AmwgSampler(params, poisreg_post(ld, mcmc, K), data, {"chains": 32, "seed": 9, "faithful": True})
+    assert s.program_summary()[-1] == f"plate GENERIC n={n} body=LD_POIS"
+    s.burn(40)
+    got = s.sample(30)
+    ref = orc.run_model("pois_reg", {"y": yy, "X": X}, params, chains=32, seed=9, burn=40, sample=30)
+    assert np.array_equal(got["beta"], ref["beta"])
+    s = mcmc.AmwgSampler(params, poisreg_post(ld, mcmc, K), data, {"chains": 4096, "seed": 10})
+    assert s.program_summary()[-1] == f"plate POIS_LOGLIN n={n} K={K}"
+    s.burn(1200)
+    fast = s.sample(1)["beta"][0]
+    ref = orc.run_model("pois_reg", {"y": yy, "X": X}, params, chains=512, seed=10, burn=1200, sample=1)["beta"][0]
+    from scipy import stats
+    for k in range(K):
+        assert stats.ks_2samp(fast[:, k], ref[:, k]).statistic < 0.08, k
+    assert np.all(np.abs(fast.mean(axis=0) - beta_true) < 0.25)
+
+
+def test_data_larger_than_shared_memory_is_served_from_l2(gpu_pkg):
+    """N = 40000 fp64 (320 KB > the 200 KB staging budget): the column stays in global memory; same posterior as a run on
+    the sufficient statistics would give (exact Normal-model posterior mean of mu = xbar to prior shrinkage)."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(50.0, 3.0, 40000)
+    s = gpu_pkg.mcmc.AmwgSampler(models.PARAMS_NORM, models.norm_post_readme(gpu_pkg.ld), x.tolist(), {"chains": 2048, "seed": 1})
+    s.burn(1500)
+    d = s.sample(1)
+    assert abs(d["mu"].mean() - x.mean()) < 0.005 and abs(d["sigma"].mean() - x.std(ddof=1)) < 0.01
+    assert abs(d["mu"].std() - x.std() / np.sqrt(x.size)) < 0.004
