@@ -15,12 +15,13 @@ LIB_PATH = os.path.join(_HERE, "libamwg_b200.so")
 # ---- opcodes / plate kinds: keep in sync with include/amwg.h (checked by tests/test_abi.py) ----
 _OPS = """END CONST COMP DATA DATA_I COMP_I ADD SUB MUL DIV NEG LOG EXP SQRT ABS POW LT LE GT GE EQ NE AND OR NOT SELECT
 LGAMMA LFACTORIAL LCHOOSE LBETA LD_NORM LD_UNIF LD_BETA LD_BERN LD_POIS LD_CAUCHY LD_LAPLACE LD_GAMMA LD_INVGAMMA
-LD_LNORM LD_PARETO LD_T LD_WEIBULL LD_LOGIS LD_EXP LD_BINOM LD_NBINOM LD_HYPER ACC PLATE STORE LOOP_BEGIN LOOP_END""".split()
+LD_LNORM LD_PARETO LD_T LD_WEIBULL LD_LOGIS LD_EXP LD_BINOM LD_NBINOM LD_HYPER ACC PLATE STORE LOOP_BEGIN LOOP_END
+NORM_K UNIF_K BETA_K""".split()
 OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)
 REAL, INT, BINARY = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class AmwgParam(C.Structure):

@@ -275,22 +275,6 @@ __device__ __noinline__ double cold_op(int op, double x, double y, double z, dou
   }
 }
 
-// number of value operands (A..D) of each opcode
-__device__ __forceinline__ int op_arity(int op) {
-  if (op <= AMWG_OP_COMP_I) return 0;
-  if (op <= AMWG_OP_DIV) return 2;                    // ADD SUB MUL DIV
-  if (op <= AMWG_OP_ABS) return 1;                    // NEG LOG EXP SQRT ABS
-  if (op <= AMWG_OP_OR) return 2;                     // POW LT LE GT GE EQ NE AND OR
-  if (op == AMWG_OP_NOT) return 1;
-  if (op == AMWG_OP_SELECT) return 3;
-  if (op <= AMWG_OP_LFACTORIAL) return 1;             // LGAMMA LFACTORIAL
-  if (op <= AMWG_OP_LBETA) return 2;                  // LCHOOSE LBETA
-  if (op == AMWG_OP_LD_BERN || op == AMWG_OP_LD_POIS || op == AMWG_OP_LD_EXP) return 2;
-  if (op == AMWG_OP_LD_T || op == AMWG_OP_LD_HYPER) return 4;
-  if (op <= AMWG_OP_LD_HYPER) return 3;
-  return 0;                                           // ACC PLATE STORE LOOP_* END fetch their own
-}
-
 __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalState& es, int pc,
                                            double* der, bool want_top) {
   double stk[kStack];
@@ -312,11 +296,13 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
     const int a = (int)(w >> 17);
     // operands, last one first (the order inline words are laid out and stack operands are popped)
     double x = 0.0, y = 0.0, z = 0.0, t = 0.0;
-    const int nops = op_arity(op);
-    if (nops >= 4) AMWG_OPND(t, (w >> 14) & 3);
-    if (nops >= 3) AMWG_OPND(z, (w >> 12) & 3);
-    if (nops >= 2) AMWG_OPND(y, (w >> 10) & 3);
-    if (nops >= 1) AMWG_OPND(x, (w >> 8) & 3);
+    if (op != AMWG_OP_PLATE) {                          // plates fetch their own operands
+      const int mD = (w >> 14) & 3, mC = (w >> 12) & 3, mB = (w >> 10) & 3, mA = (w >> 8) & 3;
+      if (mD != AMWG_MODE_NONE) AMWG_OPND(t, mD);
+      if (mC != AMWG_MODE_NONE) AMWG_OPND(z, mC);
+      if (mB != AMWG_MODE_NONE) AMWG_OPND(y, mB);
+      if (mA != AMWG_MODE_NONE) AMWG_OPND(x, mA);
+    }
     double r = 0.0;
     bool has_r = true;
     switch (op) {
@@ -349,6 +335,9 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
       case AMWG_OP_OR: r = (x != 0.0 || y != 0.0) ? 1.0 : 0.0; break;
       case AMWG_OP_NOT: r = x != 0.0 ? 0.0 : 1.0; break;
       case AMWG_OP_SELECT: r = x != 0.0 ? y : z; break;
+      case AMWG_OP_NORM_K: { double d = x - y; r = z - (d * d) / t; break; }
+      case AMWG_OP_UNIF_K: r = (x < y || x > z) ? -CUDART_INF : t; break;
+      case AMWG_OP_BETA_K: r = (x > 1 || x < 0) ? -CUDART_INF : (y * js_log(x) + z * js_log(1 - x)) - t; break;
       case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
       case AMWG_OP_PLATE: {
         has_r = false;
@@ -999,10 +988,12 @@ extern "C" int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scal
 
 extern "C" int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device) {
   if (n <= 0) return 0;
-  if (op <= AMWG_OP_COMP_I || op >= AMWG_OP_ACC || arity < 1 || arity > 4) return fail("amwg_ld_eval: bad opcode or arity");
+  if (op <= AMWG_OP_COMP_I || (op >= AMWG_OP_ACC && op < AMWG_OP_NORM_K) || op >= AMWG_OP__COUNT || arity < 1 || arity > 4)
+    return fail("amwg_ld_eval: bad opcode or arity");
   CUDA_TRY(cudaSetDevice(device));
   const int c = AMWG_MODE_CONST;
-  int word = AMWG_WORD(op, c, arity > 1 ? c : 0, arity > 2 ? c : 0, arity > 3 ? c : 0, 0, 0);
+  const int none = AMWG_MODE_NONE;
+  int word = AMWG_WORD(op, c, arity > 1 ? c : none, arity > 2 ? c : none, arity > 3 ? c : none, 0, 0);
   double *d_args = nullptr, *d_out = nullptr;
   CUDA_TRY(cudaMalloc(&d_args, sizeof(double) * (size_t)n * arity));
   if (cudaMalloc(&d_out, sizeof(double) * (size_t)n) != cudaSuccess) { cudaFree(d_args); return fail("amwg_ld_eval: cudaMalloc failed"); }

@@ -280,13 +280,13 @@ class DataObject(dict):
 # ------------------------------------------------------------------------------------------------
 _MIN_PLATE = 8          # shorter runs stay unrolled scalar terms
 MAX_IMMEDIATE = 32767
-MODE_STACK, MODE_CONST, MODE_COMP = 0, 1, 2
+MODE_STACK, MODE_CONST, MODE_COMP, MODE_NONE = 0, 1, 2, 3
 _ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, "SQRT": 1, "ABS": 1, "POW": 2,
           "LT": 2, "LE": 2, "GT": 2, "GE": 2, "EQ": 2, "NE": 2, "AND": 2, "OR": 2, "NOT": 1, "SELECT": 3,
           "LGAMMA": 1, "LFACTORIAL": 1, "LCHOOSE": 2, "LBETA": 2,
           "LD_NORM": 3, "LD_UNIF": 3, "LD_BETA": 3, "LD_BERN": 2, "LD_POIS": 2, "LD_CAUCHY": 3, "LD_LAPLACE": 3,
           "LD_GAMMA": 3, "LD_INVGAMMA": 3, "LD_LNORM": 3, "LD_PARETO": 3, "LD_T": 4, "LD_WEIBULL": 3, "LD_LOGIS": 3,
-          "LD_EXP": 2, "LD_BINOM": 3, "LD_NBINOM": 3, "LD_HYPER": 4}
+          "LD_EXP": 2, "LD_BINOM": 3, "LD_NBINOM": 3, "LD_HYPER": 4, "NORM_K": 4, "UNIF_K": 4, "BETA_K": 4}
 
 
 class Program:
@@ -318,12 +318,12 @@ class Program:
         self.consts.append(float("nan"))       # filled by amwg_fold_kernel at create
         return len(self.consts) - 1
 
-    def emit(self, op: str, operand: int = 0, *extra: int, modes=(0, 0, 0, 0), acc: bool = False):
+    def emit(self, op: str, operand: int = 0, *extra: int, modes=(), acc: bool = False):
         """One instruction word (include/amwg.h): opcode | operand modes A..D | ACC flag | 15-bit immediate, + extra words."""
         operand = int(operand)
         if not 0 <= operand <= MAX_IMMEDIATE:
             raise JsThrow("log_post is too large for the device program format (immediate > 32767)")
-        m = list(modes) + [0] * (4 - len(modes))
+        m = list(modes) + [MODE_NONE] * (4 - len(modes))
         self.code.append(OP[op] | (m[0] << 8) | (m[1] << 10) | (m[2] << 12) | (m[3] << 14) | ((1 if acc else 0) << 16) | (operand << 17))
         self.code.extend(int(e) for e in extra)
 
@@ -398,16 +398,42 @@ def _or(a: Sym, b: Sym) -> Sym:
     return Sym("OR", (a, b))
 
 
+def _is_const(n: Sym) -> bool:
+    stack = [n]
+    while stack:
+        m = stack.pop()
+        if m.op in ("COMP", "DATA_I", "COMP_I"):
+            return False
+        stack.extend(m.args)
+    return True
+
+
+def _const_value(n: Sym):
+    """numeric value of a literal leaf (CONST), else None"""
+    return n.val if n.op == "CONST" else None
+
+
 def _expand_ld(op: str, a: Tuple[Sym, ...]) -> Optional[Sym]:
     log = Math.log
     if op == "LD_NORM":                                   # distributions.js:119-121
         x, mean, sd = a
-        return _c(-0.5) * log(_c(2) * _c(Math.PI)) - log(sd) - Math.pow(x - mean, 2) / (_c(2) * sd * sd)
+        k1 = _c(-0.5) * log(_c(2) * _c(Math.PI)) - log(sd)
+        k2 = _c(2) * sd * sd
+        if _is_const(sd):                                 # constant sd (a prior): one fused op, K1/K2 folded on the device
+            return Sym("NORM_K", (x, mean, k1, k2))
+        return k1 - Math.pow(x - mean, 2) / k2
     if op == "LD_UNIF":                                   # :221-223
         x, mn, mx = a
-        return where(_or(x < mn, x > mx), _NEG_INF, log(_c(1) / (mx - mn)))
+        k = log(_c(1) / (mx - mn))
+        if _is_const(mn) and _is_const(mx):
+            return Sym("UNIF_K", (x, mn, mx, k))
+        return where(_or(x < mn, x > mx), _NEG_INF, k)
     if op == "LD_BETA":                                   # :104-113
         x, s1, s2 = a
+        if _const_value(s1) is not None and _const_value(s2) is not None:
+            if _const_value(s1) == 1 and _const_value(s2) == 1:
+                return where(_or(x > 1, x < 0), _NEG_INF, 0.0)
+            return Sym("BETA_K", (x, s1 - 1, s2 - 1, Sym("LBETA", (s1, s2))))
         body = (s1 - 1) * log(x) + (s2 - 1) * log(_c(1) - x) - Sym("LBETA", (s1, s2))
         return where(_or(x > 1, x < 0), _NEG_INF, where(Sym("AND", (s1 == 1, s2 == 1)), 0.0, body))
     if op == "LD_BERN":                                   # :228-230

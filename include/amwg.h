@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 3
+#define AMWG_ABI_VERSION 4
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -67,7 +67,8 @@ typedef struct {
  * log_post(state, data) (mcmc.js:958-960) arrives as a postfix program over an fp64 stack.
  * Instruction word (int32):
  *     bits  0-7   opcode
- *     bits  8-9   mode of operand A     0 = popped from the stack, 1 = consts[next word], 2 = state component [next word]
+ *     bits  8-9   mode of operand A     0 = popped from the stack, 1 = consts[next word], 2 = state component [next word],
+ *                                       3 = the opcode has no such operand
  *     bits 10-11  mode of operand B     (operands are named in source order: op(A, B, C, D))
  *     bits 12-13  mode of operand C
  *     bits 14-15  mode of operand D
@@ -83,6 +84,7 @@ typedef struct {
 #define AMWG_MODE_STACK 0
 #define AMWG_MODE_CONST 1
 #define AMWG_MODE_COMP 2
+#define AMWG_MODE_NONE 3
 #define AMWG_WORD(op, mA, mB, mC, mD, acc, a) \
   ((int32_t)((uint32_t)(op) | ((uint32_t)(mA) << 8) | ((uint32_t)(mB) << 10) | ((uint32_t)(mC) << 12) | ((uint32_t)(mD) << 14) | \
              ((uint32_t)((acc) ? 1 : 0) << 16) | ((uint32_t)(a) << 17)))
@@ -110,6 +112,11 @@ enum {
   AMWG_OP_STORE,        /* derived[operand] = pop   (derived-quantity program only)          */
   AMWG_OP_LOOP_BEGIN,   /* start of a GENERIC plate body: i = 0 (plate[a].n points); next word: offset to continue at when n == 0 */
   AMWG_OP_LOOP_END,     /* lp = lp + pop; if (++i < n) jump to the word offset in the next word (first word of the body) */
+  /* ld.* with constant hyper-parameters, partially evaluated by the host: the constant parts are folded once on the device
+   * (fold table), the rest is the same operations in the same order as distributions.js -> same bits as the LD_* opcode. */
+  AMWG_OP_NORM_K,       /* (x, mean, K1, K2): K1 - pow(x-mean,2)/K2,  K1 = -0.5*log(2pi) - log(sd), K2 = 2*sd*sd   (:119-121) */
+  AMWG_OP_UNIF_K,       /* (x, min, max, K):  (x<min || x>max) ? -inf : K,  K = log(1/(max-min))                    (:221-223) */
+  AMWG_OP_BETA_K,       /* (x, a1, b1, K):    (x>1 || x<0) ? -inf : a1*log(x) + b1*log(1-x) - K, a1 = shape1-1, b1 = shape2-1, K = lbeta (:104-113) */
   AMWG_OP__COUNT
 };
 

@@ -79,6 +79,14 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
             r = UN[op](opnd(mA))
         elif op == "SELECT":
             z = opnd(mC); y = opnd(mB); x = opnd(mA); r = y if x != 0 else z
+        elif op in ("NORM_K", "UNIF_K", "BETA_K"):
+            t = opnd(mD); z = opnd(mC); y = opnd(mB); x = opnd(mA)
+            if op == "NORM_K":
+                d = x - y; r = z - div(d * d, t)
+            elif op == "UNIF_K":
+                r = -math.inf if (x < y or x > z) else t
+            else:
+                r = -math.inf if (x > 1 or x < 0) else (y * O.orc_log(x) + z * O.orc_log(1 - x)) - t
         elif op.startswith("LD_"):
             n = {"LD_BERN": 2, "LD_POIS": 2, "LD_EXP": 2, "LD_T": 4, "LD_HYPER": 4}.get(op, 3)
             args = [opnd(m) for m in (mA, mB, mC, mD)[:n][::-1]][::-1]
