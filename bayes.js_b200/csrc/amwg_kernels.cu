@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(128) amwg_ld_kernel(int word, int arity, const
     int nc = 0;
     code[nc++] = word;
     for (int k = arity - 1; k >= 0; --k) code[nc++] = k;      // inline operand words: last operand first
-    code[nc++] = AMWG_OP_END;
+    code[nc++] = AMWG_WORD(AMWG_OP_END, AMWG_MODE_NONE, AMWG_MODE_NONE, AMWG_MODE_NONE, AMWG_MODE_NONE, 0, 0);
   }
   if (i < n) for (int k = 0; k < arity; ++k) consts[threadIdx.x * 4 + k] = args[i * arity + k];
   __syncthreads();
