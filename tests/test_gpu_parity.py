@@ -174,20 +174,16 @@ def test_adaptation_and_info_match_oracle(gpu_pkg, orc):
 
 
 def test_chain_sharding_invariance(gpu_pkg):
-    """Chain g's draws depend on (seed, g) only: two handles over [0,64) and [64,128) reproduce one handle over [0,128)."""
+    """Chain g's draws depend on (seed, g) only: a handle over chains [64, 128) reproduces that block of a handle over [0, 128)
+    -- what makes results independent of how chains are sharded over GPUs (parallel.shard_bounds picks first_chain)."""
+    from bayes_js_b200.parallel import shard_bounds
     y = config3_data()
     mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
     full = mcmc.AmwgSampler(models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y.tolist()}, {"chains": 128, "seed": 4})
     a = full.sample(60)
-    import os
-    os.environ["RANK"], os.environ["WORLD_SIZE"] = "1", "2"
-    try:
-        # `distributed` sharding without a process group: shard_chains reads RANK/WORLD_SIZE
-        s1 = mcmc.AmwgSampler(models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y.tolist()}, {"chains": 128, "seed": 4, "distributed": True})
-        assert (s1.first_chain, s1.local_chains) == (64, 64)
-        s1.distributed = False                # sample locally, no gather
-        b = s1.sample(60)
-    finally:
-        del os.environ["RANK"], os.environ["WORLD_SIZE"]
+    first, count = shard_bounds(128, 1, 2)
+    assert (first, count) == (64, 64)
+    half = mcmc.AmwgSampler(models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y.tolist()}, {"chains": count, "seed": 4, "first_chain": first})
+    b = half.sample(60)
     assert np.array_equal(a["theta"][:, 64:], b["theta"])
     assert np.array_equal(a["m"][:, 64:], b["m"])
