@@ -17,6 +17,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -39,6 +40,10 @@ constexpr int kStack = 16;
 #define AMWG_THREADS 128
 #endif
 constexpr int kThreads = AMWG_THREADS;
+#ifndef AMWG_SYNC_THREADS
+#define AMWG_SYNC_THREADS 128
+#endif
+constexpr int kSyncThreads = AMWG_SYNC_THREADS;   // CTA size of the phase-synchronised sweep kernel
 constexpr int kAdaptChunk = 64;
 constexpr unsigned kSmemBudget = 200u * 1024u;   // bytes of dynamic shared memory we are willing to fill with data
 
@@ -53,6 +58,7 @@ struct ModelDev {
   int n_columns, n_plates, n_params, D, n_derived;
   int logpost_prog, derived_prog;
   const unsigned char* adapting;   // [D] global, host-maintained (start/stop_adaptation)
+  int phase_sync;                  // 1: every chain takes the same number of steps per sweep -> CTA-wide phase barriers are legal
 };
 
 struct ChainArrays {
@@ -482,18 +488,26 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
 }
 
 // ---- K1: n_sweeps Sampler.step()s per chain, samples recorded before each kept sweep --------------------------------
+// Phase synchronisation: when every chain takes the same number of steps per sweep (all parameters scalar, or a single
+// parameter), the CTA runs propose / evaluate / accept in lock step (__syncthreads between phases). Warps that share a
+// scheduler then execute the same few hundred instructions together (instruction-cache hits instead of every warp streaming
+// the whole sweep body past the others), while the CTAs resident on one SM drift apart and overlap their fp64 loops with each
+// other's bookkeeping. Threads past the last chain shadow chain C-1 and write nothing, so they can take part in the barriers.
 #ifndef AMWG_MINBLOCKS
 #define AMWG_MINBLOCKS 5
 #endif
-__global__ void __launch_bounds__(kThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
+__global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ Ctx ctx;
   __shared__ __align__(8) unsigned long long bar;
   stage_model(m, smem, ctx, &bar);
 
-  const unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= a.C) return;
   const unsigned long long C = a.C;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = tid < C;
+  const bool sync = m.phase_sync != 0;
+  if (!valid && !sync) return;
+  const unsigned long long chain = valid ? tid : C - 1;
   double* st = a.state + chain;
   const double* psd = a.psd + chain;
   int* acc = a.acc + chain;
@@ -507,7 +521,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(Mo
 
   for (long long s = 0; s < sa.n_sweeps; ++s) {
     // -- Sampler.sample: record the state BEFORE stepping (mcmc.js:1021-1027)
-    if (sa.record) {
+    if (sa.record && valid) {
       long long i = sa.sample_i0 + s;
       if (i % sa.thin == 0) {
         long long row = i / sa.thin;
@@ -546,6 +560,8 @@ __global__ void __launch_bounds__(kThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(Mo
         }
       }
       for (int r = 0; r < n_rounds; ++r) {
+        // ---- phase 1: propose
+        if (sync) __syncthreads();
         int c = pa.comp_offset;
         if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
         const unsigned long long ci = (unsigned long long)c * C;
@@ -561,35 +577,43 @@ __global__ void __launch_bounds__(kThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(Mo
           if (pa.type == AMWG_INT) prop = js_round(prop);
           need = !(prop < pa.lower || prop > pa.upper);
         }
-        __syncwarp(__activemask());
+        // ---- phase 2: evaluate log_post at the proposal (the O(N) likelihood sum)
+        if (sync) __syncthreads(); else __syncwarp(__activemask());
         double lp_new = 0.0;
         if (need) {
           EvalState es{st, C, c, prop};
           lp_new = eval_logpost(ctx, es, m.logpost_prog);
         }
+        // ---- phase 3: accept / reject
+        if (sync) __syncthreads();
         if (pa.type == AMWG_BINARY) {
           // BinaryStepper.step (mcmc.js:753-767); log_post of the current value is the cached one
           double z0raw = (cur == 0.0) ? curr : lp_new, z1raw = (cur == 0.0) ? lp_new : curr;
           double mx = js_max(z0raw, z1raw);
           double z0 = z0raw - mx, z1 = z1raw - mx;
           double zero_prob = js_exp(z0 - js_log(js_exp(z0) + js_exp(z1)));
-          if (g.next() < zero_prob) { st[ci] = 0.0; curr = z0raw; }
-          else { st[ci] = 1.0; curr = z1raw; }
+          bool zero = g.next() < zero_prob;
+          if (valid) st[ci] = zero ? 0.0 : 1.0;
+          curr = zero ? z0raw : z1raw;
         } else if (need) {
           // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
           double accept_prob = js_exp(lp_new - curr);
           if (accept_prob > g.next()) {
-            st[ci] = prop;
             curr = lp_new;
-            if (m.adapting[c]) acc[ci] += 1;
+            if (valid) {
+              st[ci] = prop;
+              if (m.adapting[c]) acc[ci] += 1;
+            }
           }
         }
       }
     }
   }
-  a.rng_n[chain] = g.n;
-  a.perm[chain] = perm;
-  a.curr_lp[chain] = curr;
+  if (valid) {
+    a.rng_n[chain] = g.n;
+    a.perm[chain] = perm;
+    a.curr_lp[chain] = curr;
+  }
 }
 
 // ---- K2: Roberts-Rosenthal batch update of prop_log_scale (mcmc.js:538-550), a follow-on kernel -----------------------
@@ -811,6 +835,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   m.image = d_image;
   m.n_columns = md->n_columns; m.n_plates = md->n_plates; m.n_params = md->n_params; m.D = md->n_comp;
   m.n_derived = md->n_derived; m.logpost_prog = md->logpost_prog; m.derived_prog = md->derived_prog;
+  {
+    bool all_scalar = true;
+    for (int p = 0; p < md->n_params; ++p) all_scalar = all_scalar && md->params[p].n_comp == 1;
+    m.phase_sync = (all_scalar || md->n_params == 1) ? 1 : 0;
+    if (const char* e = getenv("AMWG_PHASE_SYNC")) m.phase_sync = m.phase_sync && atoi(e) != 0;
+  }
 
   unsigned smem_used = m.image_bytes;
   for (int k = 0; k < md->n_columns; ++k) {
@@ -881,7 +911,10 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       s->ev_pool.emplace_back(e0, e1);
     }
     CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].first, s->stream));
-    amwg_sweep_kernel<<<grid_for(C, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    {
+      const int threads = s->m.phase_sync ? kSyncThreads : kThreads;
+      amwg_sweep_kernel<<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].second, s->stream));
     n_events++;
