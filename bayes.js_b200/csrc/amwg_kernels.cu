@@ -163,7 +163,7 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
 // per block read as four 16-byte warp-broadcast loads (ld.shared.v2.f64 when `saddr` != 0, i.e. the column sits in shared
 // memory; else the same loop over global/L2 addresses). AMWG_PREFETCH: the next block is loaded while the current one is summed.
 #ifndef AMWG_NACC
-#define AMWG_NACC 8
+#define AMWG_NACC 4
 #endif
 #ifndef AMWG_PREFETCH
 #define AMWG_PREFETCH 1
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
 // the whole sweep body past the others), while the CTAs resident on one SM drift apart and overlap their fp64 loops with each
 // other's bookkeeping. Threads past the last chain shadow chain C-1 and write nothing, so they can take part in the barriers.
 #ifndef AMWG_MINBLOCKS
-#define AMWG_MINBLOCKS 5
+#define AMWG_MINBLOCKS 7
 #endif
 __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -616,6 +616,10 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
   }
 }
 
+}  // namespace amwg
+#include "amwg_wide.cuh"
+namespace amwg {
+
 // ---- K2: Roberts-Rosenthal batch update of prop_log_scale (mcmc.js:538-550), a follow-on kernel -----------------------
 struct AdaptArgs {
   int c0, n;
@@ -719,6 +723,7 @@ struct amwg_sampler {
   double* d_out = nullptr; size_t d_out_bytes = 0;
   int* d_monitor = nullptr; int d_monitor_cap = 0;
   long long launches = 0;
+  int chains_per_thread = 1;                  // 1: amwg_sweep_kernel; 2 / 4: amwg_sweep_kernel_wide<W>
   double last_sweep_ms = 0.0;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 };
@@ -852,7 +857,13 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     else m.col_smem_off[k] = -1;       // too large for shared memory: served from L2 (streamed tiles: DESIGN.md "next")
   }
   s->smem_bytes = smem_used;
-  if (cudaFuncSetAttribute(amwg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+  // chains per thread: 1. The W = 2 / 4 variants (amwg_wide.cuh) execute 22 % fewer instructions per chain-step but need 168
+  // registers (12 warps/SM) and measure 0.77x / 0.61x on config 2 (profiles/r01w); AMWG_CHAINS_PER_THREAD selects them for experiments.
+  s->chains_per_thread = 1;
+  if (const char* e = getenv("AMWG_CHAINS_PER_THREAD")) { int w = atoi(e); if (w == 1 || w == 2 || w == 4) s->chains_per_thread = w; }
+  if (cudaFuncSetAttribute(amwg_sweep_kernel_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_sweep_kernel_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
@@ -911,7 +922,11 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       s->ev_pool.emplace_back(e0, e1);
     }
     CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].first, s->stream));
-    {
+    if (s->chains_per_thread == 2) {
+      amwg_sweep_kernel_wide<2><<<grid_for((C + 1) / 2, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    } else if (s->chains_per_thread == 4) {
+      amwg_sweep_kernel_wide<4><<<grid_for((C + 3) / 4, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    } else {
       const int threads = s->m.phase_sync ? kSyncThreads : kThreads;
       amwg_sweep_kernel<<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
     }
