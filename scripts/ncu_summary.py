@@ -60,7 +60,7 @@ def main():
         kern = m.get("Kernel Name", ("", ""))[1].split("(")[0].split("::")[-1]
         funcs = []
         for ln in elf.splitlines():
-            mm = re.match(r"\s+0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+\S+\s+\$_ZN4amwg\d+" + kern + r"\S*?\$(\S+)", ln)
+            mm = re.match(r"\s+0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+\S+\s+\$_ZN4amwg" + str(len(kern)) + kern + r"E[^$]*\$(\S+)", ln)
             if mm:
                 funcs.append((int(mm.group(1), 16) // 16, int(mm.group(2), 16) // 16, mm.group(3)))
         funcs.sort()
