@@ -45,6 +45,7 @@ constexpr int kThreads = AMWG_THREADS;
 #endif
 constexpr int kSyncThreads = AMWG_SYNC_THREADS;   // CTA size of the phase-synchronised sweep kernel
 constexpr int kAdaptChunk = 64;
+constexpr long long kHostChunkSweeps = 10;       // sample() to a host buffer: sweeps per launch, so copies overlap compute at this granularity
 constexpr unsigned kSmemBudget = 200u * 1024u;   // bytes of dynamic shared memory we are willing to fill with data
 
 // ---- model image as the kernels see it (passed by value) ------------------------------------------------------
@@ -915,6 +916,7 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       if (!(need >= 1.0)) need = 1.0;
       if (need < (double)L) L = (long long)need;
     }
+    if (record && host_out && L > kHostChunkSweeps) L = kHostChunkSweeps;   // finer launches: the D2H of finished rows trails the sweeps closely
     SweepArgs sa{L, i0, thin, record, n_monitor, d_monitor, d_out};
     if (n_events >= s->ev_pool.size()) {
       cudaEvent_t e0, e1;

@@ -174,7 +174,7 @@ class DataVec:
     def __getitem__(self, i):
         inner = self._inner()
         if isinstance(i, PlateIndex):
-            if i.n != self._shape[0] and len(self._shape) == 1 and i.n > self._shape[0]:
+            if i.n > self._shape[0]:
                 raise JsThrow("plate index runs past the end of a data array")
             if len(self._shape) == 1:
                 return Sym("DATA_I", (), (self._col, self._off, 1, i.plate_id))
@@ -331,7 +331,6 @@ class Program:
 class Tracer:
     def __init__(self):
         self.columns: List[np.ndarray] = []
-        self._col_ids: Dict[int, int] = {}
         self._n_plate_idx = 0
         self.plate_sizes: Dict[int, int] = {}
 
