@@ -312,6 +312,9 @@ class AmwgSampler(Sampler):
         self.seed = int.from_bytes(os.urandom(8), "little") if seed is None else int(seed) & 0xFFFFFFFFFFFFFFFF
         self.device = int(get_option("device", options, _default_device()))
         self.distributed = bool(get_option("distributed", options, False))
+        self.gather = get_option("gather", options, "all")                # distributed sample(): "all" | "root" | "none"
+        if self.gather not in ("all", "root", "none"):
+            raise JsThrow("options.gather must be \"all\", \"root\" or \"none\"")
         self.faithful = bool(get_option("faithful", options, False))      # no factorised plates: bit-faithful sums, slower
 
         # flat component layout: Object.keys(params) order, row-major inside a parameter

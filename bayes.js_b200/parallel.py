@@ -61,9 +61,29 @@ def all_gather_chain_axis(local, counts):
     return out.index_select(-1, keep)
 
 
+def gather_chain_axis_to_root(local, counts, root: int = 0):
+    """Gather `local[rows, entries, c_rank]` over the chain axis onto rank `root` only (returns None elsewhere):
+    the host-memory-friendly variant when one process collects the draws."""
+    import torch
+    import torch.distributed as dist
+    ws, rank = dist.get_world_size(), dist.get_rank()
+    rows, entries = local.shape[0], local.shape[1]
+    cmax = max(counts)
+    if len(set(counts)) > 1:
+        full = all_gather_chain_axis(local, counts)          # ragged shards: reuse the padded all-gather
+        return full if rank == root else None
+    local = local.contiguous()
+    out = torch.empty((rows, entries, ws * cmax), dtype=local.dtype, device=local.device) if rank == root else None
+    for r in range(rows):
+        for e in range(entries):
+            dist.gather(local[r, e], list(out[r, e].view(ws, cmax).unbind(0)) if rank == root else None, dst=root)
+    return out
+
+
 def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) -> np.ndarray:
-    """sample() on this rank's shard into a device buffer, all-gather over the chain axis (NCCL over NVLink), then one
-    D2H into a pinned host buffer. Returns [rows, n_entries, total_chains] on every rank."""
+    """sample() on this rank's shard into a device buffer, collect over the chain axis (NCCL over NVLink), then one D2H into
+    a pinned host buffer. `sampler.gather`: "all" (default; every rank returns all chains), "root" (rank 0 returns all chains,
+    the other ranks their own shard), "none" (every rank returns its own shard)."""
     import torch
     import torch.distributed as dist
     from . import _ffi
@@ -80,7 +100,15 @@ def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) ->
         raise JsThrow(L.amwg_last_error().decode())
     ws = dist.get_world_size()
     counts = [shard_bounds(sampler.n_chains, r, ws)[1] for r in range(ws)]
-    full = all_gather_chain_axis(local, counts)
+    mode = getattr(sampler, "gather", "all")
+    if mode == "all":
+        full = all_gather_chain_axis(local, counts)
+    elif mode == "root":
+        full = gather_chain_axis_to_root(local, counts, 0)
+        if full is None:
+            full = local
+    else:
+        full = local
     host = _pinned_empty(tuple(full.shape))
     torch.from_numpy(host).copy_(full, non_blocking=True)
     torch.cuda.synchronize(dev)

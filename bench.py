@@ -163,7 +163,7 @@ def run_ours(args):
     chains_total = args.chains * world
     iters = args.iters
     sampler = mcmc.AmwgSampler(PARAMS, make_log_post(ld), config2_data().tolist(),
-                               {"chains": chains_total, "seed": 0, "device": local_rank, "distributed": world > 1})
+                               {"chains": chains_total, "seed": 0, "device": local_rank, "distributed": world > 1, "gather": "root"})
     local = sampler.local_chains
     sampler.burn(args.burn)
     mon = np.array([0, 1], dtype=np.int32)
@@ -197,7 +197,7 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
 
     # ---- e2e: public API, host arrays ---------------------------------------------------------------------------
-    e2e_steps = max(1, min(args.steps, 5))
+    e2e_steps = max(1, min(args.steps, 5 if world == 1 else 3))
     w1 = sampler.sample(iters)                 # warm-up: two live results = the two pinned buffers the loop alternates between
     w2 = sampler.sample(iters)
     del w1, w2
@@ -207,7 +207,7 @@ def run_ours(args):
         draws = sampler.sample(iters)
     barrier()
     dt_e2e = time.perf_counter() - t1
-    assert draws["mu"].shape == (iters, chains_total)
+    assert draws["mu"].shape == (iters, chains_total if rank == 0 else local)      # gather="root": rank 0 holds every chain
 
     times = torch.tensor([dt, dt_e2e, kernel_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
@@ -244,7 +244,7 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "draws/s", "h2d_bytes_per_step": int(mon.nbytes),
                     "d2h_bytes_per_step": int(iters * 2 * chains_total * 8), "steps": e2e_steps,
                     "note": "mcmc.AmwgSampler.sample(): pinned host buffer, D2H overlapped with the sweeps"
-                            + ("; NCCL all-gather of the shards first" if world > 1 else "")},
+                            + ("; NCCL gather of the shards to rank 0 first (gather=\"root\": one host copy of all draws)" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu:

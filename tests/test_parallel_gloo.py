@@ -26,7 +26,7 @@ def _worker(rank, world, port, n_chains, q):
     import torch.distributed as dist
     import __graft_entry__ as graft
     graft.load_package()
-    from bayes_js_b200.parallel import all_gather_chain_axis, shard_bounds, shard_chains, world as world_fn
+    from bayes_js_b200.parallel import all_gather_chain_axis, gather_chain_axis_to_root, shard_bounds, shard_chains, world as world_fn
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         assert world_fn() == (rank, world)
@@ -39,7 +39,9 @@ def _worker(rank, world, port, n_chains, q):
         full = all_gather_chain_axis(local, counts)
         gg = torch.arange(0, n_chains, dtype=torch.float64)
         want = torch.stack([torch.stack([gg * 10 + r + 0.5 * e for e in range(entries)]) for r in range(rows)])
-        q.put((rank, bool(torch.equal(full, want)), tuple(full.shape)))
+        rooted = gather_chain_axis_to_root(local, counts, 0)
+        ok_root = (rooted is None) if rank != 0 else bool(torch.equal(rooted, want))
+        q.put((rank, bool(torch.equal(full, want)) and ok_root, tuple(full.shape)))
     finally:
         dist.destroy_process_group()
 
