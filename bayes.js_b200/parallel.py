@@ -81,9 +81,9 @@ def gather_chain_axis_to_root(local, counts, root: int = 0):
 
 
 def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) -> np.ndarray:
-    """sample() on this rank's shard into a device buffer, collect over the chain axis (NCCL over NVLink), then one D2H into
-    a pinned host buffer. `sampler.gather`: "all" (default; every rank returns all chains), "root" (rank 0 returns all chains,
-    the other ranks their own shard), "none" (every rank returns its own shard)."""
+    """Distributed sample(): this rank's shard is sampled in row chunks; while chunk k+1 is being computed, chunk k is collected
+    over the chain axis (NCCL over NVLink) and copied into a pinned host buffer on a side stream. `sampler.gather`: "all"
+    (default; every rank returns all chains), "root" (rank 0 returns all chains, the others their own shard), "none" (own shard)."""
     import torch
     import torch.distributed as dist
     from . import _ffi
@@ -93,23 +93,40 @@ def sample_and_gather(sampler, n: int, thin: int, mon: np.ndarray, rows: int) ->
         raise JsThrow("options.distributed needs an initialised torch.distributed process group")
     L = _ffi.lib()
     dev = torch.device("cuda", sampler.device)
-    local = torch.empty((rows, len(mon), sampler.local_chains), dtype=torch.float64, device=dev)
-    torch.cuda.synchronize(dev)
-    rc = L.amwg_sample_device(sampler._handle, n, thin, mon.ctypes.data_as(C.POINTER(C.c_int32)), len(mon), local.data_ptr())
-    if rc != 0:
-        raise JsThrow(L.amwg_last_error().decode())
-    ws = dist.get_world_size()
+    ws, rank = dist.get_world_size(), dist.get_rank()
     counts = [shard_bounds(sampler.n_chains, r, ws)[1] for r in range(ws)]
     mode = getattr(sampler, "gather", "all")
-    if mode == "all":
-        full = all_gather_chain_axis(local, counts)
-    elif mode == "root":
-        full = gather_chain_axis_to_root(local, counts, 0)
-        if full is None:
-            full = local
-    else:
-        full = local
-    host = _pinned_empty(tuple(full.shape))
-    torch.from_numpy(host).copy_(full, non_blocking=True)
-    torch.cuda.synchronize(dev)
+    collect = mode == "all" or mode == "root"
+    out_chains = sampler.n_chains if (mode == "all" or (mode == "root" and rank == 0)) else sampler.local_chains
+    host = _pinned_empty((rows, len(mon), out_chains))
+    host_t = torch.from_numpy(host)
+    monp = mon.ctypes.data_as(C.POINTER(C.c_int32))
+    chunk_rows = max(1, min(rows, 10))
+    side = torch.cuda.Stream(device=dev)
+    done_events = []
+    row0 = 0
+    while row0 < rows:
+        r = min(chunk_rows, rows - row0)
+        n_chunk = min(n - row0 * thin, r * thin)               # sample(a) then sample(b) == sample(a+b) when a is a multiple of thin
+        local = torch.empty((r, len(mon), sampler.local_chains), dtype=torch.float64, device=dev)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = L.amwg_sample_device(sampler._handle, n_chunk, thin, monp, len(mon), local.data_ptr())      # blocks until the chunk is in HBM
+        if rc != 0:
+            raise JsThrow(L.amwg_last_error().decode())
+        with torch.cuda.stream(side):                            # collect + D2H of this chunk overlap the next chunk's sweeps
+            if mode == "all":
+                full = all_gather_chain_axis(local, counts)
+            elif mode == "root":
+                full = gather_chain_axis_to_root(local, counts, 0)
+                if full is None:
+                    full = local
+            else:
+                full = local
+            host_t[row0:row0 + r].copy_(full, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(side)
+            done_events.append((ev, local, full))                # keep the device buffers alive until the copy has finished
+        row0 += r
+    side.synchronize()
+    del done_events, collect
     return host
