@@ -520,12 +520,15 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
   const int P = m.n_params;
   unsigned char order[kMaxDim0];
 
+  // `i % thin === 0` (mcmc.js:1021) without a 64-bit division per sweep: position inside the thinning interval and next row
+  long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
+  long long row = sa.record ? (sa.sample_i0 + sa.thin - 1) / sa.thin : 0;
   for (long long s = 0; s < sa.n_sweeps; ++s) {
     // -- Sampler.sample: record the state BEFORE stepping (mcmc.js:1021-1027)
-    if (sa.record && valid) {
-      long long i = sa.sample_i0 + s;
-      if (i % sa.thin == 0) {
-        long long row = i / sa.thin;
+    if (sa.record) {
+      const bool rec_now = rec_phase == 0;
+      if (++rec_phase == sa.thin) rec_phase = 0;
+      if (rec_now && valid) {
         double der[kMaxDerived];
         bool have_der = false;
         for (int j = 0; j < sa.n_monitor; ++j) {
@@ -540,6 +543,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
         }
       }
+      if (rec_now) ++row;
     }
     // -- AmwgStepper.step: shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
     for (int i = P - 1; i > 0; --i) {

@@ -1,4 +1,5 @@
-// amwg_wide.cuh -- the sweep kernel with W chains per thread (W = 2 by default for large chain counts).
+// amwg_wide.cuh -- EXPERIMENTAL variant of the sweep kernel with W chains per thread (off by default, AMWG_CHAINS_PER_THREAD=2|4).
+// Bit-exact with the default kernel (the GPU test-suite passes with W = 2 and 4) but slower on B200: see DESIGN.md section 4.
 //
 // Same semantics as amwg_sweep_kernel (every chain is still an independent run of the reference under its own Philox stream);
 // what changes is the mapping: thread t owns chains t, t+T, ... (T = threads), and walks them together, so that
@@ -302,12 +303,14 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
   const unsigned code_sa = smem_u32(ctx.code), consts_sa = smem_u32(ctx.consts);
   unsigned char order[W][kMaxDim0];
 
+  long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
+  long long row = sa.record ? (sa.sample_i0 + sa.thin - 1) / sa.thin : 0;
   for (long long s = 0; s < sa.n_sweeps; ++s) {
     // -- Sampler.sample: record the state BEFORE stepping (mcmc.js:1021-1027)
     if (sa.record) {
-      long long i = sa.sample_i0 + s;
-      if (i % sa.thin == 0) {
-        long long row = i / sa.thin;
+      const bool rec_now = rec_phase == 0;
+      if (++rec_phase == sa.thin) rec_phase = 0;
+      if (rec_now) {
 #pragma unroll
         for (int k = 0; k < W; ++k) {
           if (!valid[k]) continue;
@@ -325,6 +328,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
             sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain[k]] = v;
           }
         }
+        ++row;
       }
     }
     // -- AmwgStepper.step: shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
