@@ -21,7 +21,7 @@ OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)
 REAL, INT, BINARY = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class AmwgParam(C.Structure):
@@ -53,7 +53,9 @@ class AmwgModel(C.Structure):
                 ("n_consts", C.c_int32), ("consts", C.POINTER(C.c_double)),
                 ("n_columns", C.c_int32), ("columns", C.POINTER(AmwgColumn)),
                 ("n_plates", C.c_int32), ("plates", C.POINTER(AmwgPlate)),
-                ("n_fold", C.c_int32), ("fold_prog", C.POINTER(C.c_int32)), ("fold_dst", C.POINTER(C.c_int32))]
+                ("n_fold", C.c_int32), ("fold_prog", C.POINTER(C.c_int32)), ("fold_dst", C.POINTER(C.c_int32)),
+                ("n_variant_comps", C.c_int32), ("variant_comps", C.POINTER(C.c_int32)),
+                ("variant_logpost", C.POINTER(C.c_int32)), ("variant_derived", C.POINTER(C.c_int32))]
 
 
 EXPORTS = ["amwg_create", "amwg_destroy", "amwg_burn", "amwg_sample", "amwg_sample_device", "amwg_get_state",

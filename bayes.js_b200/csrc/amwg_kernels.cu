@@ -60,6 +60,10 @@ struct ModelDev {
   int logpost_prog, derived_prog;
   const unsigned char* adapting;   // [D] global, host-maintained (start/stop_adaptation)
   int phase_sync;                  // 1: every chain takes the same number of steps per sweep -> CTA-wide phase barriers are legal
+  int n_variant_comps;             // binary components whose value selects the program (amwg_model.variant_*), 0 = single program
+  int variant_comps[AMWG_MAX_VARIANT_COMPS];
+  int variant_logpost[1 << AMWG_MAX_VARIANT_COMPS];
+  int variant_derived[1 << AMWG_MAX_VARIANT_COMPS];
 };
 
 struct ChainArrays {
@@ -442,6 +446,18 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
 #undef AMWG_OPND
 }
 
+// which recorded configuration of the binary components applies to this evaluation state (0 when the model has one program)
+__device__ __forceinline__ int variant_of(const ModelDev& m, const EvalState& es) {
+  int v = 0;
+  for (int k = 0; k < m.n_variant_comps; ++k) v |= (es.comp(m.variant_comps[k]) != 0.0) ? (1 << k) : 0;
+  return v;
+}
+__device__ __forceinline__ int logpost_pc(const ModelDev& m, const EvalState& es) {
+  return m.n_variant_comps ? m.variant_logpost[variant_of(m, es)] : m.logpost_prog;
+}
+__device__ __forceinline__ int derived_pc(const ModelDev& m, const EvalState& es) {
+  return m.n_variant_comps ? m.variant_derived[variant_of(m, es)] : m.derived_prog;
+}
 __device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
   return run_program(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, nullptr, false);
 }
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
   a.perm[chain] = perm;
   a.rng_n[chain] = 0;
   EvalState es{a.state + chain, a.C, -1, 0.0};
-  a.curr_lp[chain] = eval_logpost(ctx, es, m.logpost_prog);
+  a.curr_lp[chain] = eval_logpost(ctx, es, logpost_pc(m, es));
 }
 
 // ---- K1: n_sweeps Sampler.step()s per chain, samples recorded before each kept sweep --------------------------------
@@ -537,7 +553,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           if (e < m.D) {
             v = st[(unsigned long long)e * C];
           } else {
-            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_ctx(ctx, es, m.derived_prog, der, false); have_der = true; }
+            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_ctx(ctx, es, derived_pc(m, es), der, false); have_der = true; }
             v = der[e - m.D];
           }
           sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
@@ -587,7 +603,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         double lp_new = 0.0;
         if (need) {
           EvalState es{st, C, c, prop};
-          lp_new = eval_logpost(ctx, es, m.logpost_prog);
+          lp_new = eval_logpost(ctx, es, logpost_pc(m, es));
         }
         // ---- phase 3: accept / reject
         if (sync) __syncthreads();
@@ -659,7 +675,7 @@ __global__ void __launch_bounds__(kThreads) amwg_derived_kernel(ModelDev m, Chai
   if (chain >= a.C) return;
   double der[kMaxDerived];
   EvalState es{a.state + chain, a.C, -1, 0.0};
-  run_ctx(ctx, es, m.derived_prog, der, false);
+  run_ctx(ctx, es, derived_pc(m, es), der, false);
   for (int d = 0; d < m.n_derived; ++d) out[(unsigned long long)d * a.C + chain] = der[d];
 }
 
@@ -776,6 +792,11 @@ static int validate_model(const amwg_model* md) {
   }
   if (D != md->n_comp) return fail("amwg_create: n_comp does not match the parameter list");
   if (md->logpost_prog < 0 || md->logpost_prog >= md->n_code) return fail("amwg_create: logpost_prog out of range");
+  if (md->n_variant_comps < 0 || md->n_variant_comps > AMWG_MAX_VARIANT_COMPS) return fail("amwg_create: at most 4 program-selecting binary components are supported");
+  for (int k = 0; k < md->n_variant_comps; ++k)
+    if (md->variant_comps[k] < 0 || md->variant_comps[k] >= D) return fail("amwg_create: variant component out of range");
+  for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v)
+    if (md->variant_logpost[v] < 0 || md->variant_logpost[v] >= md->n_code) return fail("amwg_create: variant program out of range");
   if (md->n_derived > 0 && (md->derived_prog < 0 || md->derived_prog >= md->n_code)) return fail("amwg_create: derived_prog out of range");
   for (int k = 0; k < md->n_fold; ++k)
     if (md->fold_prog[k] < 0 || md->fold_prog[k] >= md->n_code || md->fold_dst[k] < 0 || md->fold_dst[k] >= md->n_consts)
@@ -845,6 +866,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   m.image = d_image;
   m.n_columns = md->n_columns; m.n_plates = md->n_plates; m.n_params = md->n_params; m.D = md->n_comp;
   m.n_derived = md->n_derived; m.logpost_prog = md->logpost_prog; m.derived_prog = md->derived_prog;
+  m.n_variant_comps = md->n_variant_comps;
+  for (int k = 0; k < md->n_variant_comps; ++k) m.variant_comps[k] = md->variant_comps[k];
+  for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v) {
+    m.variant_logpost[v] = md->variant_logpost[v];
+    m.variant_derived[v] = md->variant_derived ? md->variant_derived[v] : -1;
+  }
   {
     bool all_scalar = true;
     for (int p = 0; p < md->n_params; ++p) all_scalar = all_scalar && md->params[p].n_comp == 1;

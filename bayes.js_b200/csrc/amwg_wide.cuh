@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
             if (e < m.D) {
               v = es.st[k][(unsigned long long)e * C];
             } else {
-              if (!have_der) { EvalState e1{es.st[k], C, -1, 0.0}; run_ctx(ctx, e1, m.derived_prog, der, false); have_der = true; }
+              if (!have_der) { EvalState e1{es.st[k], C, -1, 0.0}; run_ctx(ctx, e1, derived_pc(m, e1), der, false); have_der = true; }
               v = der[e - m.D];
             }
             sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain[k]] = v;
@@ -395,7 +395,17 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
 #pragma unroll
         for (int k = 0; k < W; ++k) lp_new[k] = 0.0;
         __syncwarp(__activemask());
-        if (any) run_logpost_w<W>(code_sa, consts_sa, ctx, es, m.logpost_prog, lp_new);
+        if (any) {
+          if (m.n_variant_comps == 0) {
+            run_logpost_w<W>(code_sa, consts_sa, ctx, es, m.logpost_prog, lp_new);
+          } else {                                   // program depends on each chain's binary configuration: evaluate chain by chain
+#pragma unroll
+            for (int k = 0; k < W; ++k) {
+              EvalState e1{es.st[k], C, es.moved[k], es.val[k]};
+              lp_new[k] = eval_logpost(ctx, e1, logpost_pc(m, e1));
+            }
+          }
+        }
         // ---- accept / reject
 #pragma unroll
         for (int k = 0; k < W; ++k) {

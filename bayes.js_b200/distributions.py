@@ -10,6 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import _ffi
+from . import tracer as _tracer
 from .tracer import JsThrow, Math, Sym, is_sym, lift, where
 
 __all__ = ["lgamma", "lfactorial", "lchoose", "lbeta", "beta", "cauchy", "norm", "bivarnorm", "laplace", "dexp", "gamma",
@@ -32,7 +33,7 @@ def _op(op: str, arity: int, cite: str):
     def f(*args):
         if len(args) != arity:
             raise JsThrow(f"ld.{op[3:].lower() if op.startswith('LD_') else op.lower()} takes {arity} arguments")
-        if any(is_sym(a) for a in args):
+        if any(is_sym(a) for a in args) or _tracer._ACTIVE:      # inside log_post: record (constants are folded on the device)
             return Sym(op, tuple(lift(a) for a in args))
         return _device_eval(op, args)
     f.__doc__ = f"distributions.js:{cite}"

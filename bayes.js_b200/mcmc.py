@@ -390,7 +390,14 @@ class AmwgSampler(Sampler):
         m.n_fold = len(prog.fold_prog)
         m.fold_prog = fold_prog.ctypes.data_as(C.POINTER(C.c_int32))
         m.fold_dst = fold_dst.ctypes.data_as(C.POINTER(C.c_int32))
-        self._model_keepalive = (prm, init, opts, code, consts, cols, plates, fold_prog, fold_dst, m)
+        vcomps = np.asarray(prog.variant_comps if prog.variant_comps else [0], dtype=np.int32)
+        vlp = np.asarray(prog.variant_logpost if prog.variant_logpost else [0], dtype=np.int32)
+        vder = np.asarray(prog.variant_derived if prog.variant_derived else [-1], dtype=np.int32)
+        m.n_variant_comps = len(prog.variant_comps)
+        m.variant_comps = vcomps.ctypes.data_as(C.POINTER(C.c_int32))
+        m.variant_logpost = vlp.ctypes.data_as(C.POINTER(C.c_int32))
+        m.variant_derived = vder.ctypes.data_as(C.POINTER(C.c_int32))
+        self._model_keepalive = (prm, init, opts, code, consts, cols, plates, fold_prog, fold_dst, vcomps, vlp, vder, m)
         L = _ffi.lib()
         h = C.c_void_p()
         rc = L.amwg_create(C.byref(m), self.local_chains, self.first_chain, self.seed, self.device, C.byref(h))

@@ -36,6 +36,11 @@ class JsThrow(Exception):
         self.message = message
 
 
+class NeedsConcrete(JsThrow):
+    """log_post used a symbolic value where Python needs a concrete one (`if m == 0:`). When only binary parameters are
+    involved the tracer retries with those parameters concrete, once per configuration (see trace())."""
+
+
 # ------------------------------------------------------------------------------------------------
 # symbolic values
 # ------------------------------------------------------------------------------------------------
@@ -71,11 +76,14 @@ class Sym:
     __hash__ = object.__hash__
 
     def __bool__(self):
-        raise JsThrow("log_post branches on a parameter value, which cannot be traced for the device; "
-                      "use mcmc.where(cond, a, b)")
+        raise NeedsConcrete("log_post branches on a parameter value, which cannot be traced for the device; "
+                            "use mcmc.where(cond, a, b)")
 
     def __float__(self):
-        raise JsThrow("log_post converts a parameter to a Python float (e.g. math.log); use mcmc.Math.* / ld.*")
+        raise NeedsConcrete("log_post converts a parameter to a Python float (e.g. math.log); use mcmc.Math.* / ld.*")
+
+    def __index__(self):
+        raise NeedsConcrete("log_post uses a parameter value as an index; only binary parameters can be used that way")
 
     def __repr__(self):
         if self.op == "CONST": return f"{self.val!r}"
@@ -243,7 +251,7 @@ class ParamVec:
         if not 0 <= i < self._shape[0]:
             return Sym("CONST", (), float("nan"))
         if len(self._shape) == 1:
-            return Sym("COMP", (), self._c0 + i)
+            return self._t.comp(self._c0 + i)
         return ParamVec(self._t, self._c0 + i * inner, self._shape[1:])
 
     def __iter__(self):
@@ -301,6 +309,9 @@ class Program:
         self.logpost_prog = 0
         self.derived_prog = -1
         self.derived_names: List[str] = []
+        self.variant_comps: List[int] = []     # binary components whose configuration selects the program (amwg.h variant_*)
+        self.variant_logpost: List[int] = []
+        self.variant_derived: List[int] = []
         self.fold_prog: List[int] = []         # word offsets of constant sub-expression programs (evaluated once on the device)
         self.fold_dst: List[int] = []          # ... and the consts[] slot each one fills
         self.summary: List[str] = []           # human-readable: what each term became
@@ -333,6 +344,11 @@ class Tracer:
         self.columns: List[np.ndarray] = []
         self._n_plate_idx = 0
         self.plate_sizes: Dict[int, int] = {}
+        self.concrete: Dict[int, float] = {}   # component -> value, for binary components traced per configuration
+
+    def comp(self, c: int):
+        """state component c as the closure sees it: symbolic, or a plain number when traced per configuration"""
+        return self.concrete[c] if c in self.concrete else Sym("COMP", (), c)
 
     # -- data -----------------------------------------------------------------------------------
     def add_column(self, arr: np.ndarray) -> int:
@@ -375,7 +391,7 @@ class Tracer:
         for name, p in params.items():
             dim = list(p["dim"])
             if dim == [1]:
-                st[name] = Sym("COMP", (), offsets[name])
+                st[name] = self.comp(offsets[name])
             else:
                 st[name] = ParamVec(self, offsets[name], tuple(dim))
         return st
@@ -705,8 +721,10 @@ class Lowering:
         return xcol, len(terms), base
 
     # -- main -------------------------------------------------------------------------------------
-    def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
+    def add_logpost(self, result: Sym, derived: Dict[str, Sym]) -> Tuple[int, int]:
+        """Emit one log_post program (and its derived-quantity program); returns their word offsets (derived: -1 if none)."""
         p = self.prog
+        lp_off = len(p.code)
         terms = _spine_terms(result)
         i = 0
         n_terms = len(terms)
@@ -727,22 +745,32 @@ class Lowering:
             p.summary.append(f"term {tm.op}")
             i += 1
         p.emit("END")
-        # derived quantities
+        der_off = -1
         if derived:
-            p.derived_prog = len(p.code)
+            der_off = len(p.code)
+            names = list(derived.keys())
+            if p.derived_names and p.derived_names != names:
+                raise JsThrow("log_post adds different derived quantities for different values of the binary parameters")
+            p.derived_names = names
             for d, (name, expr) in enumerate(derived.items()):
                 self.emit_expr(lift(expr))
                 p.emit("STORE", d)
-                p.derived_names.append(name)
             p.emit("END")
-        # constant sub-expression programs, in creation order (a later one may read an earlier slot)
+        return lp_off, der_off
+
+    def finish(self) -> Program:
+        """constant sub-expression programs, in creation order (a later one may read an earlier slot)"""
+        p = self.prog
         for k, tree in self._fold_trees:
             p.fold_prog.append(len(p.code))
             p.fold_dst.append(k)
             self.emit_expr(tree, prepare=False)
             p.emit("END")
-        p.logpost_prog = 0
         return p
+
+    def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
+        self.prog.logpost_prog, self.prog.derived_prog = self.add_logpost(result, derived)
+        return self.finish()
 
     def _find_run(self, terms: List[Sym], i0: int):
         """Longest run starting at i0 of terms equal up to data positions that advance affinely. -> (body, length)."""
@@ -839,11 +867,11 @@ def _lfactorial_host(y: float) -> float:
     return math.log(2.5066282746310005 * ser / xx) - tmp
 
 
-def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: int, data, faithful: bool = False) -> Tuple[Program, List[str]]:
-    """Run `log_post` once symbolically; return the lowered program and the derived-quantity names."""
-    tr = Tracer()
+MAX_VARIANT_COMPS = 4
+
+
+def _run_closure(tr: Tracer, log_post, params, offsets, wrapped):
     state = tr.make_state(params, offsets)
-    wrapped = tr.wrap_data(data)
     _ACTIVE.append(tr)
     try:
         result = log_post(state, wrapped)
@@ -856,7 +884,40 @@ def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: in
     for k, v in derived.items():
         if not isinstance(v, (Sym, numbers.Real)):
             raise JsThrow(f"derived quantity {k} must be a number")
-    prog = Lowering(tr, n_comp, faithful).lower(result, derived)
+    return result, derived
+
+
+def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: int, data, faithful: bool = False) -> Tuple[Program, List[str]]:
+    """Run `log_post` symbolically and return the lowered program and the derived-quantity names.
+
+    If the closure needs concrete values (Python `if` on a parameter) and the model has at most MAX_VARIANT_COMPS binary
+    components, it is recorded once per configuration of those components instead (the device picks the program that matches the
+    evaluated state, amwg.h variant_*): `if (m === 0) ... else ...` of tests/test_data.js:163-168 can be written as is."""
+    tr = Tracer()
+    wrapped = tr.wrap_data(data)
+    low = Lowering(tr, n_comp, faithful)
+    try:
+        result, derived = _run_closure(tr, log_post, params, offsets, wrapped)
+    except NeedsConcrete as exc:
+        comps = [offsets[name] + c for name, p in params.items() if p["type"] == "binary" for c in range(int(np.prod(p["dim"])))]
+        if not comps or len(comps) > MAX_VARIANT_COMPS:
+            raise JsThrow(exc.message)
+        prog = low.prog
+        prog.variant_comps = comps
+        for v in range(1 << len(comps)):
+            tr.concrete = {c: float((v >> k) & 1) for k, c in enumerate(comps)}
+            try:
+                result, derived = _run_closure(tr, log_post, params, offsets, wrapped)
+            except NeedsConcrete as exc2:
+                raise JsThrow(exc2.message)                  # branches on a real / int parameter: cannot be recorded
+            lp_off, der_off = low.add_logpost(result, derived)
+            prog.variant_logpost.append(lp_off)
+            prog.variant_derived.append(der_off)
+        tr.concrete = {}
+        prog.logpost_prog, prog.derived_prog = prog.variant_logpost[0], prog.variant_derived[0]
+        low.finish()
+        return prog, list(prog.derived_names)
+    prog = low.lower(result, derived)
     return prog, list(derived.keys())
 
 

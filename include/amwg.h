@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 4
+#define AMWG_ABI_VERSION 5
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -158,7 +158,14 @@ typedef struct {
    * device's own arithmetic, and stored into consts[fold_dst[k]]: fold_prog[k] is the word offset of an
    * END-terminated expression program.  (log(2*pi), log(sd) of a constant sd, ... : same bits, computed once.) */
   int32_t n_fold;     const int32_t* fold_prog;  const int32_t* fold_dst;
+  /* Control flow on binary parameters (`if (m === 0) ... else ...`, tests/test_data.js:163-168) cannot be recorded as one
+   * expression, so the host records log_post once per configuration of up to AMWG_MAX_VARIANT_COMPS binary components.
+   * Configuration v has bit k set when state component variant_comps[k] is non-zero (the proposal counts for the moved one);
+   * its programs start at variant_logpost[v] / variant_derived[v]. n_variant_comps == 0: logpost_prog / derived_prog are used. */
+  int32_t n_variant_comps;  const int32_t* variant_comps;
+  const int32_t* variant_logpost;  const int32_t* variant_derived;     /* 1 << n_variant_comps entries each (derived: -1 if none) */
 } amwg_model;
+#define AMWG_MAX_VARIANT_COMPS 4
 
 typedef struct amwg_sampler amwg_sampler;
 

@@ -124,3 +124,35 @@ PARAMS_COMPLEX = {"p1": {"type": "real", "lower": 0, "upper": 1}, "n1": {"type":
 BINOM_DATA = {"x": [5, 6, 9, 14, 13, 20], "n": [10, 10, 20, 20, 30, 30]}                                                                # :174
 PARAMS_HIER_BINOM = {"p": {"type": "real", "init": 0.5, "lower": 0, "upper": 1, "dim": [1, 6]},
                      "mu_logit_p": {"type": "real", "init": 0}, "sigma_logit_p": {"type": "real", "lower": 0, "init": 1}}                # :176-193
+
+
+# ---- the same models with the reference's literal control flow on the binary parameter (recorded once per configuration) ----
+def spike_bern_literal(ld):
+    def log_post(state, data):
+        theta, m = state.theta, state.m
+        log_post = 0
+        log_post += ld.beta(theta, 2, 2)
+        log_post += ld.bern(m, 0.5)
+        for i in range(len(data.x)):
+            if m == 0:
+                log_post += ld.bern(data.x[i], 0.5)
+            else:
+                log_post += ld.bern(data.x[i], theta)
+        return log_post
+    return log_post
+
+
+def complex_model_post_literal(ld):
+    def f(par, x):                                                           # tests/test_data.js:154-171, as written
+        p1, n1, m = par.p1, par.n1, par.m
+        log_post = 0
+        log_post += ld.bern(m, 0.4)
+        log_post += ld.beta(p1, 2, 2)
+        log_post += ld.nbinom(n1, 2, 0.1)
+        for i in range(len(x)):
+            if m == 0:
+                log_post += ld.nbinom(x[i], 21, 0.5)
+            else:
+                log_post += ld.nbinom(x[i], n1, p1)
+        return log_post
+    return f

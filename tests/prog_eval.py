@@ -140,4 +140,11 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
 
 
 def logpost(prog, consts, state, O, moved=-1, val=0.0):
-    return run(prog, consts, state, prog.logpost_prog, O, moved=moved, val=val)
+    pc = prog.logpost_prog
+    if prog.variant_comps:                      # program selected by the configuration of the binary components
+        v = 0
+        for k, c in enumerate(prog.variant_comps):
+            x = val if c == moved else float(state[c])
+            v |= (1 << k) if x != 0 else 0
+        pc = prog.variant_logpost[v]
+    return run(prog, consts, state, pc, O, moved=moved, val=val)

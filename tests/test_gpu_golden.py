@@ -59,3 +59,26 @@ def test_gpu_ld_matches_the_js_bit_for_bit(gpu_pkg):
         want = np.array([float.fromhex(r[1]) for r in rows])
         got = getattr(ld, fname)(*[args[:, k] for k in range(args.shape[1])])
         assert gu.same(got, want), fname
+
+
+@pytest.mark.parametrize("case", [c for c in G["samplers"] if c["log_post"] in ("spike_bern", "complex_model_post")],
+                         ids=lambda c: f"{c['name']}-chain{c['chain']}")
+def test_literal_if_on_a_binary_parameter_matches_the_js(case, gpu_pkg):
+    """The reference's `if (m === 0) ... else ...` (tests/test_data.js:163-168) written as a plain Python `if`: log_post is
+    recorded once per value of m and the device picks the program that matches the evaluated state. Same draws as mcmc.js."""
+    import models
+    _c, _py, params, data, _dc = gu.resolve_case(case, gpu_pkg)
+    literal = models.spike_bern_literal(gpu_pkg.ld) if case["log_post"] == "spike_bern" else models.complex_model_post_literal(gpu_pkg.ld)
+    opts = copy.deepcopy(case["options"]) or {}
+    opts.update({"seed": case["seed"], "first_chain": case["chain"], "chains": 1})
+    s = gpu_pkg.mcmc.AmwgSampler(copy.deepcopy(params), literal, data, opts)
+    assert len(s._program.variant_logpost) == 2
+    results = iter(case["results"])
+    for step in case["script"]:
+        if step[0] == "burn": s.burn(step[1])
+        elif step[0] == "thin": s.thin(step[1])
+        elif step[0] == "sample":
+            want = gu.unhex(next(results)["draws"])
+            got = s.sample(step[1])
+            for k in want:
+                assert gu.same(got[k], want[k]), (case["name"], k)

@@ -159,11 +159,36 @@ def test_hierarchical_and_regression_plates(pkg, orc):
     assert abs(prog_eval.logpost(prog, consts, st, orc.lib()) - ref) <= 1e-11 * abs(ref)
 
 
+def test_control_flow_on_binary_parameters_is_recorded_per_configuration(pkg, orc):
+    """`if (m === 0) ... else ...` (tests/test_data.js:163-168) written as a plain Python `if`: one program per value of m,
+    each bit-faithful to the oracle's C model."""
+    y = config3_data()
+    prog, _, _ = _trace(pkg, models.spike_bern_literal(pkg.ld), models.PARAMS_SPIKE, {"x": y.tolist()})
+    assert prog.variant_comps == [1] and len(prog.variant_logpost) == 2
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    rng = np.random.default_rng(4)
+    for _ in range(20):
+        st = [rng.uniform(0.01, 0.99), float(rng.integers(0, 2))]
+        ref, _ = _oracle_logpost(orc, "spike_bern", {"x": y}, models.PARAMS_SPIKE, st)
+        assert prog_eval.logpost(prog, consts, st, orc.lib()) == ref
+        other = 1.0 - st[1]                       # the binary stepper evaluates the other value of m as the "moved" component
+        ref2, _ = _oracle_logpost(orc, "spike_bern", {"x": y}, models.PARAMS_SPIKE, [st[0], other])
+        assert prog_eval.logpost(prog, consts, st, orc.lib(), moved=1, val=other) == ref2
+    x = [float(v) for v in np.random.default_rng(7).negative_binomial(21, 0.5, 12)]
+    prog, _, _ = _trace(pkg, models.complex_model_post_literal(pkg.ld), models.PARAMS_COMPLEX, x)
+    assert prog.variant_comps == [2]
+    consts = prog_eval.fold_constants(prog, orc.lib())
+    for m in (0.0, 1.0):
+        st = [0.37, 4.0, m]
+        ref, _ = _oracle_logpost(orc, "complex", {"x": np.array(x)}, models.PARAMS_COMPLEX, st)
+        assert prog_eval.logpost(prog, consts, st, orc.lib()) == ref
+
+
 def test_untraceable_closures_throw(pkg):
     ld, mcmc = pkg.ld, pkg.mcmc
 
     def branches(state, data):
-        if state.m == 0:                             # tests/test_data.js:163 pattern, written with a Python `if`
+        if state.theta > 0.5:                        # control flow on a REAL parameter cannot be recorded
             return ld.bern(1, 0.5)
         return ld.bern(1, state.theta)
     with pytest.raises(pkg.JsThrow, match="use mcmc.where"):
