@@ -13,8 +13,9 @@ the postfix program of include/amwg.h:
 * keys the closure adds to ``state`` (``par.var = sigma*sigma``, tests/test_data.js:89) become
   derived quantities.
 
-Python control flow on a symbolic value cannot be traced (``if m == 0`` with a parameter m): use
-``where(cond, a, b)``.  Such closures raise ``JsThrow`` -- there is no CPU fallback.
+Python control flow on a BINARY parameter (``if m == 0:``) is handled by recording the closure once per
+configuration of the binary components (see trace()); control flow on a real / int parameter cannot be
+recorded: use ``where(cond, a, b)``.  Such closures raise ``JsThrow`` -- there is no CPU fallback.
 """
 from __future__ import annotations
 
