@@ -303,6 +303,10 @@ class AmwgSampler(Sampler):
     """mcmc.js:1090-1099 -- the AMWG sampler, `options["chains"]` chains at once on one B200."""
 
     # -- construction ---------------------------------------------------------------------------
+    def _resolve_options(self, params, options):
+        """AmwgStepper's per-parameter option merge (mcmc.js:871-878); the stand-alone steppers read `options` directly."""
+        return resolve_stepper_options(params, options)
+
     def create_stepper_ensamble(self, params, state, log_post, options):
         options = options if options is not None else {}
         self.n_chains = int(get_option("chains", options, 1))
@@ -325,7 +329,7 @@ class AmwgSampler(Sampler):
             n_comp += int(np.prod(self.params[name]["dim"]))
         self.n_comp = n_comp
 
-        resolved = resolve_stepper_options(self.params, options)
+        resolved = self._resolve_options(self.params, options)
         self._program, self._derived_names = trace(self._user_log_post, self.params, self._offsets, n_comp, self.data, self.faithful)
 
         # shard the chains when running one process per GPU (torch.distributed, see parallel.py)
@@ -584,18 +588,210 @@ def _pinned_empty(shape) -> np.ndarray:
     return _PINNED.get(shape)
 
 
-def _not_on_device(name):
-    def ctor(*a, **k):
-        raise JsThrow(name + " is not provided as a stand-alone stepper by the device build; use mcmc.AmwgSampler")
-    ctor.__name__ = name
-    return ctor
+# ------------------------------------------------------------------------------------------------
+# stand-alone steppers -- mcmc.js:433-912 (the export list of mcmc.js:1103-1117)
+# ------------------------------------------------------------------------------------------------
+def _resolve_direct(params: Dict[str, dict], options: Optional[dict]) -> Dict[str, Dict[str, list]]:
+    """Option handling of the stepper constructors themselves: get_option / get_multidim_option on `options`
+    (mcmc.js:500-505, 644-649) -- no AmwgStepper merge."""
+    out: Dict[str, Dict[str, list]] = {}
+    for name, param in params.items():
+        r: Dict[str, list] = {}
+        if param["type"] != "binary":
+            for key, default in _STEPPER_OPTIONS:
+                if array_equal(param["dim"], [1]):
+                    r[key] = [get_option(key, options, default)]
+                else:
+                    r[key] = _flatten(get_multidim_option(key, options, param["dim"], default))
+        out[name] = r
+    return out
 
 
-# export list of mcmc.js:1103-1117 (stand-alone steppers are SURVEY 8(f).4 "next")
-RealMetropolisStepper = _not_on_device("RealMetropolisStepper")
-IntMetropolisStepper = _not_on_device("IntMetropolisStepper")
-MultiRealComponentMetropolisStepper = _not_on_device("MultiRealComponentMetropolisStepper")
-MultiIntComponentMetropolisStepper = _not_on_device("MultiIntComponentMetropolisStepper")
-BinaryStepper = _not_on_device("BinaryStepper")
-BinaryComponentStepper = _not_on_device("BinaryComponentStepper")
-AmwgStepper = _not_on_device("AmwgStepper")
+def _set_nested(dst, src):
+    """copy a nested array into an existing nested list IN PLACE (the reference's steppers mutate state[name][i]...)"""
+    for i, v in enumerate(src):
+        if isinstance(v, (list, np.ndarray)) and isinstance(dst[i], list):
+            _set_nested(dst[i], v)
+        else:
+            dst[i] = float(v)
+
+
+class _SteppedModel(AmwgSampler):
+    """The device machinery of AmwgSampler behind a zero-argument `log_post` that closes over the caller's `state` object:
+    the closure is recorded by temporarily putting symbolic values into `state`."""
+
+    def __init__(self, params, state, log_post, options, direct_options: bool):
+        self._user_state, self._zero_arg_log_post, self._direct = state, log_post, direct_options
+        names = list(params.keys())
+
+        def recorded(sym_state, _data):
+            saved = {n: state[n] for n in names}
+            try:
+                for n in names:
+                    state[n] = sym_state[n]
+                return log_post()
+            finally:
+                for n in names:
+                    state[n] = saved[n]
+        p = copy.deepcopy(params)
+        for n in names:
+            p[n]["init"] = copy.deepcopy(state[n])          # a stepper starts from the state it is given, not from params.init
+        sampler_options = {k: v for k, v in (options or {}).items()}
+        Sampler.__init__(self, p, recorded, None, sampler_options)
+
+    def _resolve_options(self, params, options):
+        stepper_options = {k: v for k, v in (options or {}).items() if k not in ("chains", "seed", "device", "first_chain", "faithful")}
+        return _resolve_direct(params, stepper_options) if self._direct else resolve_stepper_options(params, stepper_options)
+
+    def advance(self):
+        """one step; writes the new values into the caller's state object (in place for arrays) and returns them by name"""
+        self.burn(1)
+        new = self.state
+        for n in self.param_names:
+            v = new[n]
+            if isinstance(self._user_state[n], list):
+                _set_nested(self._user_state[n], np.asarray(v).tolist())
+            else:
+                self._user_state[n] = v.tolist() if isinstance(v, np.ndarray) else float(v)
+        return new
+
+
+class Stepper:
+    """mcmc.js:433-468 -- the Stepper "interface"."""
+
+    def __init__(self, params, state, log_post):
+        self.params, self.state, self.log_post = params, state, log_post
+
+    def step(self):
+        raise JsThrow("Every Stepper need to implement step()")
+
+    def start_adaptation(self):
+        pass
+
+    def stop_adaptation(self):
+        pass
+
+    def info(self):
+        return {}
+
+
+class _DeviceStepper(Stepper):
+    _type: Optional[str] = None        # proposal kind forced by the class (the reference's Real/Int steppers ignore params.type)
+    _onedim = True
+    _who = "Stepper"
+
+    def __init__(self, params, state, log_post, options=None):
+        super().__init__(params, state, log_post)
+        names = list(params.keys())
+        self._check(names, params)
+        self.param_name = names[0] if len(names) == 1 else None
+        p = complete_params(copy.deepcopy(params))
+        if self._type is not None:
+            for n in names:
+                p[n]["type"] = self._type
+                if self._type == "binary":
+                    p[n]["lower"], p[n]["upper"] = 0, 1
+        self._model = _SteppedModel(p, state, log_post, options, direct_options=self._who != "AmwgStepper")
+
+    def _check(self, names, params):
+        pass
+
+    def step(self):
+        new = self._model.advance()
+        return self.state[self.param_name] if self.param_name is not None else self.state
+
+    def start_adaptation(self):
+        self._model.start_adaptation()
+
+    def stop_adaptation(self):
+        self._model.stop_adaptation()
+
+    def _info_of(self, name):
+        per = self._model.info()["steppers"][0][name]
+        if not per:
+            return {}
+        dim = list(self._model.params[name]["dim"])
+        if dim == [1]:
+            return per
+        keys = list(per.keys())                          # nested arrays of info objects (mcmc.js:698-702)
+        flat = {k: np.asarray(per[k]).reshape(-1) for k in keys}
+        objs = [{k: flat[k][c].item() for k in keys} for c in range(int(np.prod(dim)))]
+
+        def nest(lst, d):
+            if len(d) == 1:
+                return lst
+            step = len(lst) // d[0]
+            return [nest(lst[i * step:(i + 1) * step], d[1:]) for i in range(d[0])]
+        return nest(objs, dim)
+
+    def info(self):
+        return self._info_of(self.param_name)
+
+
+class OnedimMetropolisStepper(_DeviceStepper):
+    """mcmc.js:485-571"""
+    _who = "OnedimMetropolisStepper"
+
+    def _check(self, names, params):
+        if len(names) != 1:
+            raise JsThrow("OnedimMetropolisStepper can only handle one parameter.")
+        dim = params[names[0]].get("dim", [1])
+        if not array_equal([dim] if is_number(dim) else list(dim), [1]):
+            raise JsThrow("OnedimMetropolisStepper can only handle one one-dimensional parameter.")
+
+
+class RealMetropolisStepper(OnedimMetropolisStepper):
+    """mcmc.js:586-591"""
+    _type = "real"
+
+
+class IntMetropolisStepper(OnedimMetropolisStepper):
+    """mcmc.js:605-610"""
+    _type = "int"
+
+
+class MultidimComponentMetropolisStepper(_DeviceStepper):
+    """mcmc.js:631-702"""
+    _who = "MultidimComponentMetropolisStepper"
+
+    def _check(self, names, params):
+        if len(names) != 1:
+            raise JsThrow("MultidimComponentMetropolisStepper can't handle more than one parameter.")
+
+
+class MultiRealComponentMetropolisStepper(MultidimComponentMetropolisStepper):
+    """mcmc.js:709-714"""
+    _type = "real"
+
+
+class MultiIntComponentMetropolisStepper(MultidimComponentMetropolisStepper):
+    """mcmc.js:721-726"""
+    _type = "int"
+
+
+class BinaryStepper(_DeviceStepper):
+    """mcmc.js:740-767"""
+    _type = "binary"
+    _who = "BinaryStepper"
+
+    def _check(self, names, params):
+        if len(names) != 1:
+            raise JsThrow("BinaryStepper can't handle more than one parameter.")
+
+
+class BinaryComponentStepper(_DeviceStepper):
+    """mcmc.js:781-820"""
+    _type = "binary"
+    _who = "BinaryComponentStepper"
+
+    def _check(self, names, params):
+        if len(names) != 1:
+            raise JsThrow("BinaryComponentStepper can't handle more than one parameter.")
+
+
+class AmwgStepper(_DeviceStepper):
+    """mcmc.js:837-912 -- any number of parameters; per-parameter option merge as in AmwgSampler."""
+    _who = "AmwgStepper"
+
+    def info(self):
+        return {n: self._info_of(n) for n in self._model.param_names}

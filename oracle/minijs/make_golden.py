@@ -61,6 +61,17 @@ def new_engine(seed=0, chain=0):
     it.run(open(os.path.join(REF, "distributions.js")).read())
     it.set_global("ld", mod.get("exports"))
     it.run(open(os.path.join(REF, "tests", "test_data.js")).read())    # fixtures become globals, as in the R driver (test_mcmc_js.R:33-36)
+
+    def clone(this, a):                                                 # snapshot of a live object (AmwgStepper.step returns `state` itself)
+        def cp(v):
+            if isinstance(v, JSArray): return it.new_array([cp(x) for x in v.items])
+            if isinstance(v, JSObject) and not isinstance(v, JSFunction):
+                o = it.new_object()
+                for k2, x in v.props.items(): o.put(k2, cp(x))
+                return o
+            return v
+        return cp(a[0])
+    it.set_global("JSON_clone", it.make_native("JSON_clone", clone))
     return it, st
 
 
@@ -129,6 +140,54 @@ SAMPLER_CASES = [
      {"is_adapting": True, "prop_log_scale": 2, "batch_size": 7, "params": {"mu": {"is_adapting": False, "prop_log_scale": 0, "batch_size": 0}}},
      [("burn", 30), ("sample", 20)]),
 ]
+
+
+# stand-alone steppers, as tests/test_mcmc_js.R:55-142 drives them (+ an AmwgStepper over the "complex" model, R:205-222)
+STEPPER_CASES = [
+    ("RealMetropolisStepper", "{x: {lower: -Infinity, upper: Infinity, dim:[1]}}", "{x: 0}", "norm_dens(state)", None,
+     [("step", 200)]),
+    ("IntMetropolisStepper", "{x: {lower: 0, upper: Infinity, dim:[1]}}", "{x: 1}", "poisson_dens(state)", None,
+     [("step", 300)]),
+    ("MultiRealComponentMetropolisStepper", "{x: {lower: -Infinity, upper: Infinity, dim: [2, 2]}}", "{x: [[0, 0], [0, 0]]}", "multivar_norm_dens(state)",
+     "{max_adaptation: 0.2, prop_log_scale: [[10,0],[-10, 5]]}", [("step", 100), ("stop_adaptation",), ("step", 100), ("start_adaptation",), ("step", 200)]),
+    ("MultiIntComponentMetropolisStepper", "{x: {lower: 0, upper: Infinity, dim: [2, 2]}}", "{x: [[0, 0], [0, 0]]}", "multivar_poisson_dens(state)",
+     "{batch_size: 10, target_accept_rate: [[0.22, 0.22],[0.75, 0.10]], prop_log_scale: [[1,10],[30, 1]]}",
+     [("step", 100), ("stop_adaptation",), ("step", 100), ("start_adaptation",), ("step", 200)]),
+    ("BinaryStepper", "{x: {type: 'binary'}}", "{x: 0}", "bern_dens(state)", None, [("step", 200)]),
+    ("BinaryComponentStepper", "{x: {type: 'binary', dim: [2,2]}}", "{x: [[0, 0], [0, 0]]}", "multi_bern_dens(state)", None, [("step", 150)]),
+    ("AmwgStepper", "mcmc.complete_params(params_complex_model, mcmc.param_init_fixed)", "{p1: 0.5, n1: 1, m: 1}", "complex_model_post(state, X)",
+     "{max_adaptation: 0.5, params: {p1: {max_adaptation: 0.1}}}", [("step", 150)]),
+]
+
+
+def run_stepper_case(case, seed, chain):
+    cls, params_js, state_js, post_js, options_js, script = case
+    it, st = new_engine(seed, chain)
+    it.set_global("X", to_js(it, NB12))
+    it.run(f"var parameters = {params_js}; var state = {state_js}; var posterior = function() {{ return {post_js}; }};"
+           f"var options = {options_js if options_js else 'undefined'};"
+           f"var stepper = new mcmc.{cls}(parameters, state, posterior, options);")
+    stepper = it.get_global("stepper")
+    out = {"class": cls, "seed": seed, "chain": chain, "params_js": params_js, "state_js": state_js, "posterior_js": post_js,
+           "options_js": options_js, "script": [list(x) for x in script], "results": []}
+    for step in script:
+        if step[0] == "step":
+            it.run(f"var out = []; for (var k = 0; k < {step[1]}; k++) {{ var r = stepper.step(); out.push(r === state ? JSON_clone(r) : r); }}")
+            out["results"].append(hexify(it.get_global("out")))
+        elif step[0] == "stop_adaptation":
+            it.run("stepper.stop_adaptation();")
+        else:
+            it.run("stepper.start_adaptation();")
+    if cls == "AmwgStepper":                         # info() keyed through each substepper's own name (shuffle quirk, see stepper_info)
+        info = {}
+        for sub in stepper.get("substeppers").items:
+            info[sub.get("param_name")] = hexify(it.get_prop(sub, "info").call(sub, []))
+        out["final_info"] = info
+    else:
+        out["final_info"] = hexify(it.get_prop(stepper, "info").call(stepper, []))
+    out["final_state"] = hexify(it.get_global("state"))
+    out["uniforms_consumed"] = st.n
+    return out
 
 
 def stepper_info(it, sampler):
@@ -267,6 +326,12 @@ def main():
             print("running", case[0], "chain", chain, flush=True)
             cases.append(run_sampler_case(case, seed=100 + k, chain=chain))
     G["samplers"] = cases
+    steppers = []
+    for k, case in enumerate(STEPPER_CASES):
+        for chain in (0, 3):
+            print("running stepper", case[0], "chain", chain, flush=True)
+            steppers.append(run_stepper_case(case, seed=200 + k, chain=chain))
+    G["steppers"] = steppers
     out = os.path.join(ROOT, "tests", "golden", "reference_js.json")
     with open(out, "w") as f:
         json.dump(G, f, separators=(",", ":"))

@@ -77,3 +77,35 @@ def flat_info(info_obj):
             out.extend(flat_info(x))
         return out
     return [unhex(info_obj)] if info_obj else []
+
+
+# ---- stand-alone stepper scenarios (G["steppers"]) --------------------------------------------------------------------
+NB12 = [float(v) for v in np.random.default_rng(7).negative_binomial(21, 0.5, 12)]
+
+
+def stepper_setup(case, pkg):
+    """-> dict(c_model, params, state, options, posterior(state) -> zero-arg closure, data_c) mirroring the JS text in the case."""
+    ld, mcmc = pkg.ld, pkg.mcmc
+    cls = case["class"]
+    inf = INF
+    table = {
+        "RealMetropolisStepper": dict(c_model="norm_dens", params={"x": {"lower": -inf, "upper": inf, "dim": [1]}}, state={"x": 0.0}, options=None,
+                                      model=models.norm_dens(ld), type="real"),
+        "IntMetropolisStepper": dict(c_model="poisson_dens", params={"x": {"lower": 0, "upper": inf, "dim": [1]}}, state={"x": 1.0}, options=None,
+                                     model=models.poisson_dens(ld), type="int"),
+        "MultiRealComponentMetropolisStepper": dict(c_model="multivar_norm_dens", params={"x": {"lower": -inf, "upper": inf, "dim": [2, 2]}},
+                                                    state={"x": [[0.0, 0.0], [0.0, 0.0]]}, options={"max_adaptation": 0.2, "prop_log_scale": [[10, 0], [-10, 5]]},
+                                                    model=models.multivar_norm_dens(ld), type="real"),
+        "MultiIntComponentMetropolisStepper": dict(c_model="multivar_poisson_dens", params={"x": {"lower": 0, "upper": inf, "dim": [2, 2]}},
+                                                   state={"x": [[0.0, 0.0], [0.0, 0.0]]},
+                                                   options={"batch_size": 10, "target_accept_rate": [[0.22, 0.22], [0.75, 0.10]], "prop_log_scale": [[1, 10], [30, 1]]},
+                                                   model=models.multivar_poisson_dens(ld), type="int"),
+        "BinaryStepper": dict(c_model="bern_dens", params={"x": {"type": "binary"}}, state={"x": 0.0}, options=None, model=models.bern_dens(ld), type="binary"),
+        "BinaryComponentStepper": dict(c_model="multi_bern_dens", params={"x": {"type": "binary", "dim": [2, 2]}}, state={"x": [[0.0, 0.0], [0.0, 0.0]]},
+                                       options=None, model=models.multi_bern_dens(mcmc), type="binary"),
+        "AmwgStepper": dict(c_model="complex", params=mcmc.complete_params(models.PARAMS_COMPLEX), state={"p1": 0.5, "n1": 1.0, "m": 1.0},
+                            options={"max_adaptation": 0.5, "params": {"p1": {"max_adaptation": 0.1}}}, model=None, type=None),
+    }
+    su = dict(table[cls])
+    su["data_c"] = {"x": np.asarray(NB12)} if cls == "AmwgStepper" else None
+    return su

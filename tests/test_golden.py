@@ -128,3 +128,37 @@ def test_oracle_reproduces_the_js_sampler_draw_for_draw(case, pkg, orc):
     st = s.state()
     for name, want in gu.unhex(case["final_state"]).items():
         assert gu.same(st[s.entries(name)], np.asarray(want, dtype=np.float64).reshape(-1)), name
+
+
+@pytest.mark.parametrize("case", G["steppers"], ids=lambda c: f"{c['class']}-chain{c['chain']}")
+def test_oracle_reproduces_the_js_standalone_steppers(case, pkg, orc):
+    """tests/test_mcmc_js.R:55-142 drive the steppers directly (`stepper.step()` in a loop). A stand-alone stepper over one
+    parameter consumes Math.random exactly like an AmwgSampler over that parameter (the substepper shuffle of a one-element
+    array draws nothing), so the oracle sampler reproduces every returned value."""
+    import copy as _copy
+    su = gu.stepper_setup(case, pkg)
+    m = pkg.mcmc
+    params = _copy.deepcopy(su["params"])
+    for name in params:
+        params[name]["init"] = _copy.deepcopy(su["state"][name])
+        if su["type"]:
+            params[name]["type"] = su["type"]
+    cp = m.complete_params(params)
+    resolved = (m.resolve_stepper_options if case["class"] == "AmwgStepper" else m._resolve_direct)(cp, _copy.deepcopy(su["options"]))
+    s = orc.OracleSampler(su["c_model"], su["data_c"], params, seed=case["seed"], chain=case["chain"],
+                          comp_options={n: r for n, r in resolved.items() if r})
+    results = iter(case["results"])
+    for step in case["script"]:
+        if step[0] == "stop_adaptation": s.set_adapting(False)
+        elif step[0] == "start_adaptation": s.set_adapting(True)
+        else:
+            want = gu.unhex(next(results))
+            for k in range(step[1]):
+                s.step()
+                st = s.state()
+                if case["class"] == "AmwgStepper":
+                    got = {n: st[s.entries(n)][0] for n in cp}
+                    assert got == want[k], k
+                else:
+                    assert gu.same(st[: s.D], np.asarray(want[k], dtype=np.float64).reshape(-1)), k
+    assert s.rng_position() == case["uniforms_consumed"]

@@ -82,3 +82,58 @@ def test_literal_if_on_a_binary_parameter_matches_the_js(case, gpu_pkg):
             got = s.sample(step[1])
             for k in want:
                 assert gu.same(got[k], want[k]), (case["name"], k)
+
+
+@pytest.mark.parametrize("case", G["steppers"], ids=lambda c: f"{c['class']}-chain{c['chain']}")
+def test_gpu_standalone_steppers_match_the_js(case, gpu_pkg):
+    """mcmc.RealMetropolisStepper & co used directly, as tests/test_mcmc_js.R:55-142 do: `stepper.step()` returns what the
+    reference's stepper returns, the caller's `state` object is updated in place, info() matches."""
+    import copy as _copy
+    mcmc = gpu_pkg.mcmc
+    su = gu.stepper_setup(case, gpu_pkg)
+    state = gpu_pkg.tracer.State(_copy.deepcopy(su["state"]))
+    if case["class"] == "AmwgStepper":
+        import models
+        x = gu.NB12
+        model = models.complex_model_post_literal(gpu_pkg.ld)
+        posterior = lambda: model(state, x)                                   # noqa: E731
+    else:
+        posterior = lambda: su["model"](state)                                # noqa: E731
+    opts = dict(_copy.deepcopy(su["options"]) or {})
+    opts.update({"seed": case["seed"], "first_chain": case["chain"]})
+    stepper = getattr(mcmc, case["class"])(_copy.deepcopy(su["params"]), state, posterior, opts)
+    results = iter(case["results"])
+    for step in case["script"]:
+        if step[0] == "stop_adaptation": stepper.stop_adaptation()
+        elif step[0] == "start_adaptation": stepper.start_adaptation()
+        else:
+            want = gu.unhex(next(results))
+            for k in range(step[1]):
+                r = stepper.step()
+                if case["class"] == "AmwgStepper":
+                    assert {n: float(r[n]) for n in want[k]} == want[k], k
+                else:
+                    assert gu.same(np.asarray(r, dtype=np.float64), np.asarray(want[k], dtype=np.float64)), k
+                    assert r is state["x"] or np.isscalar(r) or isinstance(r, float)
+    want_state = gu.unhex(case["final_state"])
+    for n, v in want_state.items():
+        assert gu.same(np.asarray(state[n], dtype=np.float64), np.asarray(v, dtype=np.float64)), n
+    info = stepper.info()
+    want_info = case["final_info"]
+    if case["class"] == "AmwgStepper":
+        for n in want_info:
+            for w, g in zip(gu.flat_info(want_info[n]), [info[n]] if info[n] else []):
+                assert g["prop_log_scale"] == w["prop_log_scale"] and g["batch_count"] == w["batch_count"] and g["acceptance_count"] == w["acceptance_count"]
+    else:
+        flat_g = []
+
+        def walk(o):
+            if isinstance(o, list):
+                [walk(v) for v in o]
+            elif o:
+                flat_g.append(o)
+        walk(info)
+        for w, g in zip(gu.flat_info(want_info), flat_g):
+            assert g["prop_log_scale"] == w["prop_log_scale"] and g["batch_count"] == w["batch_count"]
+            assert g["acceptance_count"] == w["acceptance_count"] and g["iterations_since_adaption"] == w["iterations_since_adaption"]
+            assert bool(g["is_adapting"]) == w["is_adapting"]
