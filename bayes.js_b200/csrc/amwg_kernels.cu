@@ -47,6 +47,8 @@ constexpr int kSyncThreads = AMWG_SYNC_THREADS;   // CTA size of the phase-synch
 constexpr int kAdaptChunk = 64;
 constexpr long long kHostChunkSweeps = 10;       // sample() to a host buffer: sweeps per launch, so copies overlap compute at this granularity
 constexpr unsigned kSmemBudget = 200u * 1024u;   // bytes of dynamic shared memory we are willing to fill with data
+constexpr unsigned kRingStageBytes = 32u * 1024u;   // TMA tile ring for columns that do not fit: 2 stages of 32 KB
+constexpr int kRingStages = 2;
 
 // ---- model image as the kernels see it (passed by value) ------------------------------------------------------
 struct ModelDev {
@@ -60,6 +62,7 @@ struct ModelDev {
   int logpost_prog, derived_prog;
   const unsigned char* adapting;   // [D] global, host-maintained (start/stop_adaptation)
   int phase_sync;                  // 1: every chain takes the same number of steps per sweep -> CTA-wide phase barriers are legal
+  int ring_smem_off;               // byte offset of the 2-stage TMA tile ring in dynamic smem, -1: every column is resident
   int n_variant_comps;             // binary components whose value selects the program (amwg_model.variant_*), 0 = single program
   int variant_comps[AMWG_MAX_VARIANT_COMPS];
   int variant_logpost[1 << AMWG_MAX_VARIANT_COMPS];
@@ -97,6 +100,9 @@ struct Ctx {                       // lives in shared memory
   const double* col[kMaxColumns];  // generic pointers (shared or global)
   unsigned col_saddr[kMaxColumns]; // 32-bit shared-window address, 0 when the column is served from global/L2
   double norm_c0;                  // -0.5 * Math.log(2 * Math.PI), evaluated once per CTA with the device's js_log
+  unsigned ring_saddr;             // shared address of the TMA tile ring (0: none, or this kernel does not run CTA-uniformly)
+  unsigned ring_uses[kRingStages]; // fills of each stage so far (mbarrier phase parity = fills & 1)
+  unsigned long long ring_bar[kRingStages];
 };
 
 struct EvalState {
@@ -137,6 +143,9 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned saddr) {
 __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* smem, Ctx& ctx, unsigned long long* bar) {
   if (threadIdx.x == 0) {
     mbar_init(bar, 1);
+    for (int k = 0; k < kRingStages; ++k) { mbar_init(&ctx.ring_bar[k], 1); ctx.ring_uses[k] = 0; }
+    // the ring needs every thread of the CTA to walk the same plates in the same order: uniform steps and a single program
+    ctx.ring_saddr = (m.ring_smem_off >= 0 && m.phase_sync && m.n_variant_comps == 0) ? smem_u32(smem + m.ring_smem_off) : 0u;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -237,6 +246,47 @@ __device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, unsig
 }
 #undef AMWG_ACC8
 
+// ---- TMA tile ring: plates over a column that does not fit in shared memory ------------------------------------------------
+// Legal only when the whole CTA walks the plate together (ModelDev.phase_sync: every chain takes the same steps per sweep and
+// evaluates every step). Thread 0 is the producer: it arms a stage's mbarrier with the tile's byte count and issues the bulk
+// copy (cp.async.bulk); all threads wait on the stage, accumulate their own chain from it (warp-broadcast LDS, same inner loop
+// as the resident case), and a CTA barrier hands the stage back to the producer, which refills it with the tile after next.
+__device__ __forceinline__ void ring_issue(Ctx& ctx, int stage, const void* src, unsigned bytes) {
+  mbar_expect_tx(&ctx.ring_bar[stage], bytes);
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ctx.ring_saddr + (unsigned)stage * kRingStageBytes),
+               "l"(src), "r"(bytes), "r"(smem_u32(&ctx.ring_bar[stage]))
+               : "memory");
+}
+
+__device__ __noinline__ double sum_sq_stream(Ctx& ctx, const double* __restrict__ gx, int n, double mean) {
+  const int tile = (int)(kRingStageBytes >> 3);                       // doubles per stage
+  const int ntiles = (n + tile - 1) / tile;
+  __syncthreads();                                                    // earlier users of the ring are done; ring_uses is stable
+  const unsigned u0 = ctx.ring_uses[0], u1 = ctx.ring_uses[1];
+  if (threadIdx.x == 0) {
+    for (int t = 0; t < 2 && t < ntiles; ++t) {
+      int cnt = min(tile, n - t * tile);
+      ring_issue(ctx, t, gx + (size_t)t * tile, (unsigned)((cnt * 8 + 15) & ~15));
+    }
+  }
+  double S = 0.0;
+  for (int t = 0; t < ntiles; ++t) {
+    const int s = t & 1;
+    mbar_wait(&ctx.ring_bar[s], ((s ? u1 : u0) + (unsigned)(t >> 1)) & 1u);
+    const int cnt = min(tile, n - t * tile);
+    const unsigned sa = ctx.ring_saddr + (unsigned)s * kRingStageBytes;
+    const double* sp = reinterpret_cast<const double*>(__cvta_shared_to_generic((size_t)sa));
+    S = S + sum_sq_dev(sp, sa, cnt, mean);
+    __syncthreads();                                                  // every warp has consumed stage s
+    if (threadIdx.x == 0 && t + 2 < ntiles) {
+      int c2 = min(tile, n - (t + 2) * tile);
+      ring_issue(ctx, s, gx + (size_t)(t + 2) * tile, (unsigned)((c2 * 8 + 15) & ~15));
+    }
+  }
+  if (threadIdx.x == 0) { ctx.ring_uses[0] = u0 + (unsigned)((ntiles + 1) >> 1); ctx.ring_uses[1] = u1 + (unsigned)(ntiles >> 1); }
+  return S;
+}
+
 __device__ __forceinline__ double norm_factorised(const Ctx& ctx, double n, double S, double sd) {
   return n * (ctx.norm_c0 - js_log(sd)) - S / (2 * sd * sd);
 }
@@ -245,7 +295,12 @@ __device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean
   const amwg_plate& pl = ctx.plates[q];
   int c = pl.col[0], off = pl.iparam[2];
   unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)off : 0u;
-  double S = sum_sq_dev(ctx.col[c] + off, sa, pl.n, mean);
+  const double* gx = ctx.col[c] + off;
+  double S;
+  if (sa == 0u && ctx.ring_saddr && (reinterpret_cast<unsigned long long>(gx) & 15ull) == 0)
+    S = sum_sq_stream(const_cast<Ctx&>(ctx), gx, pl.n, mean);          // column lives in HBM/L2: TMA tile ring
+  else
+    S = sum_sq_dev(gx, sa, pl.n, mean);
   return norm_factorised(ctx, (double)pl.n, S, sd);
 }
 
@@ -279,21 +334,59 @@ __device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const E
 
 // sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop), using log(exp(eta)) -> eta
 // and the precomputed lfactorial(y_i) column:  y*eta - exp(eta) - lfact.  (KS-level parity; real parameters only.)
-__device__ __noinline__ double plate_pois_loglin(const Ctx& ctx, int q, const EvalState& es) {
+// Rows are consumed from shared memory: resident columns directly, larger ones through the TMA tile ring
+// (stage layout: X rows | y | lfactorial, three bulk copies per stage on one mbarrier).
+__device__ __forceinline__ void pois_rows(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ lf,
+                                          int rows, int K, const double* beta, double& s0, double& s1) {
+  for (int i = 0; i < rows; ++i) {
+    double eta = 0.0;
+    const double* xr = X + (size_t)i * K;
+    for (int k = 0; k < K; ++k) eta = fma(xr[k], beta[k], eta);
+    double t = fma(y[i], eta, -exp(eta)) - lf[i];
+    if (i & 1) s1 += t; else s0 += t;
+  }
+}
+
+__device__ __noinline__ double plate_pois_loglin(const Ctx& ctx_in, int q, const EvalState& es) {
+  Ctx& ctx = const_cast<Ctx&>(ctx_in);
   const amwg_plate& pl = ctx.plates[q];
   const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
   const double* __restrict__ X = ctx.col[pl.col[1]];
   const double* __restrict__ lf = ctx.col[pl.col[2]];
-  int K = pl.iparam[1], base = pl.iparam[0];
+  const int K = pl.iparam[1], base = pl.iparam[0], n = pl.n;
   double beta[16];
   for (int k = 0; k < K && k < 16; ++k) beta[k] = es.comp(base + k);
   double s0 = 0.0, s1 = 0.0;
-  for (int i = 0; i < pl.n; ++i) {
-    double eta = 0.0;
-    for (int k = 0; k < K; ++k) eta = fma(X[(long long)i * K + k], beta[k], eta);
-    double t = fma(y[i], eta, -exp(eta)) - lf[i];
-    if (i & 1) s1 += t; else s0 += t;
+  const bool resident = ctx.col_saddr[pl.col[0]] && ctx.col_saddr[pl.col[1]] && ctx.col_saddr[pl.col[2]];
+  const bool aligned = ((reinterpret_cast<unsigned long long>(y) | reinterpret_cast<unsigned long long>(X) | reinterpret_cast<unsigned long long>(lf)) & 15ull) == 0;
+  if (resident || !ctx.ring_saddr || !aligned) {
+    pois_rows(X, y, lf, n, K, beta, s0, s1);           // shared memory (generic addressing) or, without the ring, L2
+    return s0 + s1;
   }
+  const int R = (int)((kRingStageBytes / (unsigned)((K + 2) * 8)) & ~1u);        // rows per stage (even: every piece is a multiple of 16 B)
+  const int ntiles = (n + R - 1) / R;
+  __syncthreads();
+  const unsigned u0 = ctx.ring_uses[0], u1 = ctx.ring_uses[1];
+  auto issue = [&](int t, int stage) {
+    const int r0 = t * R, rows = min(R, n - r0);
+    const unsigned bx = (unsigned)((rows * K * 8 + 15) & ~15), by = (unsigned)((rows * 8 + 15) & ~15);
+    const unsigned dst = ctx.ring_saddr + (unsigned)stage * kRingStageBytes, barsa = smem_u32(&ctx.ring_bar[stage]);
+    mbar_expect_tx(&ctx.ring_bar[stage], bx + 2u * by);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(X + (size_t)r0 * K), "r"(bx), "r"(barsa) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (unsigned)(R * K * 8)), "l"(y + r0), "r"(by), "r"(barsa) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (unsigned)(R * (K + 1) * 8)), "l"(lf + r0), "r"(by), "r"(barsa) : "memory");
+  };
+  if (threadIdx.x == 0) for (int t = 0; t < 2 && t < ntiles; ++t) issue(t, t);
+  for (int t = 0; t < ntiles; ++t) {
+    const int st = t & 1;
+    mbar_wait(&ctx.ring_bar[st], ((st ? u1 : u0) + (unsigned)(t >> 1)) & 1u);
+    const int rows = min(R, n - t * R);
+    const double* sp = reinterpret_cast<const double*>(__cvta_shared_to_generic((size_t)(ctx.ring_saddr + (unsigned)st * kRingStageBytes)));
+    pois_rows(sp, sp + (size_t)R * K, sp + (size_t)R * (K + 1), rows, K, beta, s0, s1);
+    __syncthreads();
+    if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2, st);
+  }
+  if (threadIdx.x == 0) { ctx.ring_uses[0] = u0 + (unsigned)((ntiles + 1) >> 1); ctx.ring_uses[1] = u1 + (unsigned)(ntiles >> 1); }
   return s0 + s1;
 }
 
@@ -488,20 +581,26 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
   __shared__ Ctx ctx;
   __shared__ __align__(8) unsigned long long bar;
   stage_model(m, smem, ctx, &bar);
-  unsigned long long chain = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (chain >= a.C) return;
-  for (int c = 0; c < m.D; ++c) {
-    a.state[(unsigned long long)c * a.C + chain] = init[c];
-    a.pls[(unsigned long long)c * a.C + chain] = pls0[c];
-    a.psd[(unsigned long long)c * a.C + chain] = js_exp(pls0[c]);
-    a.acc[(unsigned long long)c * a.C + chain] = 0;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = tid < a.C;
+  if (!valid && !ctx.ring_saddr) return;
+  const unsigned long long chain = valid ? tid : a.C - 1;              // shadow threads keep a streamed plate CTA-uniform
+  if (valid) {
+    for (int c = 0; c < m.D; ++c) {
+      a.state[(unsigned long long)c * a.C + chain] = init[c];
+      a.pls[(unsigned long long)c * a.C + chain] = pls0[c];
+      a.psd[(unsigned long long)c * a.C + chain] = js_exp(pls0[c]);
+      a.acc[(unsigned long long)c * a.C + chain] = 0;
+    }
+    unsigned long long perm = 0;
+    for (int p = 0; p < m.n_params; ++p) perm |= (unsigned long long)p << (4 * p);
+    a.perm[chain] = perm;
+    a.rng_n[chain] = 0;
   }
-  unsigned long long perm = 0;
-  for (int p = 0; p < m.n_params; ++p) perm |= (unsigned long long)p << (4 * p);
-  a.perm[chain] = perm;
-  a.rng_n[chain] = 0;
-  EvalState es{a.state + chain, a.C, -1, 0.0};
-  a.curr_lp[chain] = eval_logpost(ctx, es, logpost_pc(m, es));
+  // every chain starts from the same `init`: evaluate from it directly (a shadow thread must not race with the owner's writes)
+  EvalState es{init, 1, -1, 0.0};
+  double lp0 = eval_logpost(ctx, es, logpost_pc(m, es));
+  if (valid) a.curr_lp[chain] = lp0;
 }
 
 // ---- K1: n_sweeps Sampler.step()s per chain, samples recorded before each kept sweep --------------------------------
@@ -601,8 +700,8 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         // ---- phase 2: evaluate log_post at the proposal (the O(N) likelihood sum)
         if (sync) __syncthreads(); else __syncwarp(__activemask());
         double lp_new = 0.0;
-        if (need) {
-          EvalState es{st, C, c, prop};
+        if (need || ctx.ring_saddr) {                     // with the tile ring the plate is a CTA-wide collective: nobody may skip it
+          EvalState es{st, C, c, need ? prop : cur};
           lp_new = eval_logpost(ctx, es, logpost_pc(m, es));
         }
         // ---- phase 3: accept / reject
@@ -880,6 +979,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   }
 
   unsigned smem_used = m.image_bytes;
+  {   // if the columns do not all fit, reserve the TMA tile ring first, then keep resident whatever still fits
+    size_t all = m.image_bytes;
+    for (int k = 0; k < md->n_columns; ++k) all += pad16(std::max<size_t>(sizeof(double) * (size_t)md->columns[k].n, 16));
+    m.ring_smem_off = -1;
+    if (all > kSmemBudget) { m.ring_smem_off = (int)smem_used; smem_used += kRingStages * kRingStageBytes; }
+  }
   for (int k = 0; k < md->n_columns; ++k) {
     double* d_col = nullptr;
     if (dev_upload(s, md->columns[k].values, (size_t)md->columns[k].n, &d_col)) return bail(-1);

@@ -277,6 +277,8 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
   __shared__ Ctx ctx;
   __shared__ __align__(8) unsigned long long bar;
   stage_model(m, smem, ctx, &bar);
+  if (threadIdx.x == 0) ctx.ring_saddr = 0u;          // this variant does not run CTA-uniformly: columns outside shared memory come from L2
+  __syncthreads();
 
   const unsigned long long C = a.C;
   const unsigned long long T = (C + W - 1) / W;                      // threads; thread t owns chains t, t+T, ...
