@@ -983,14 +983,16 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     size_t all = m.image_bytes;
     for (int k = 0; k < md->n_columns; ++k) all += pad16(std::max<size_t>(sizeof(double) * (size_t)md->columns[k].n, 16));
     m.ring_smem_off = -1;
-    if (all > kSmemBudget) { m.ring_smem_off = (int)smem_used; smem_used += kRingStages * kRingStageBytes; }
+    // the ring is only usable by CTA-uniform models (see stage_model): do not spend shared memory (= resident CTAs) on it otherwise
+    if (all > kSmemBudget && m.phase_sync && m.n_variant_comps == 0) { m.ring_smem_off = (int)smem_used; smem_used += kRingStages * kRingStageBytes; }
   }
+  const unsigned resident_budget = m.ring_smem_off >= 0 ? 96u * 1024u : kSmemBudget;    // with the ring: keep two CTAs per SM
   for (int k = 0; k < md->n_columns; ++k) {
     double* d_col = nullptr;
     if (dev_upload(s, md->columns[k].values, (size_t)md->columns[k].n, &d_col)) return bail(-1);
     m.col_global[k] = d_col;
     m.col_bytes[k] = pad16(std::max<size_t>(sizeof(double) * (size_t)md->columns[k].n, 16));
-    if (smem_used + m.col_bytes[k] <= kSmemBudget) { m.col_smem_off[k] = (int)smem_used; smem_used += m.col_bytes[k]; }
+    if (smem_used + m.col_bytes[k] <= resident_budget) { m.col_smem_off[k] = (int)smem_used; smem_used += m.col_bytes[k]; }
     else m.col_smem_off[k] = -1;       // too large for shared memory: served from L2 (streamed tiles: DESIGN.md "next")
   }
   s->smem_bytes = smem_used;
