@@ -55,6 +55,8 @@ struct ModelDev {
   const unsigned char* image;      // global: [code | consts | plates | params] packed, 16B aligned sections
   unsigned image_bytes;            // multiple of 16
   unsigned off_code, off_consts, off_plates, off_params;
+  unsigned off_comp_prog, off_touch_off, off_touch_terms;   // dependency-aware evaluation tables (amwg_model.comp_prog ...), valid when n_terms > 0
+  int n_terms;                     // > 0: per-chain term cache in use
   const double* col_global[kMaxColumns];
   unsigned col_bytes[kMaxColumns];     // padded to 16
   int col_smem_off[kMaxColumns];       // byte offset in dynamic smem, or -1: read from global/L2
@@ -75,6 +77,8 @@ struct ChainArrays {
   double* psd;            // [D][C] exp(prop_log_scale): the proposal sd, recomputed only when pls changes (same bits as mcmc.js:578)
   int* acc;               // [D][C] acceptance_count of the current batch
   double* curr_lp;        // [C]   cached log_post(state)
+  double* tval;           // [n_terms][C] term cache: value of every value-term of log_post at the chain's current state
+  double* tcand;          // [n_terms][C] candidates written while a proposal is evaluated; committed on acceptance
   unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
   unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
   unsigned long long C;
@@ -97,6 +101,9 @@ struct Ctx {                       // lives in shared memory
   const double* consts;
   const amwg_plate* plates;
   const amwg_param* params;
+  const int* comp_prog;            // per-component programs / touched-term lists (n_terms > 0)
+  const int* touch_off;
+  const int* touch_terms;
   const double* col[kMaxColumns];  // generic pointers (shared or global)
   unsigned col_saddr[kMaxColumns]; // 32-bit shared-window address, 0 when the column is served from global/L2
   double norm_c0;                  // -0.5 * Math.log(2 * Math.PI), evaluated once per CTA with the device's js_log
@@ -110,7 +117,13 @@ struct EvalState {
   unsigned long long stride;
   int moved;          // component carrying the proposal, or -1
   double val;
+  double* tval = nullptr;     // term cache of this chain (base + chain), stride tstride; nullptr: not in use
+  double* tcand = nullptr;
+  unsigned long long tstride = 0;
+  bool direct = false;        // STORE writes the cache itself (initial full evaluation) instead of the candidate slots
   __device__ __forceinline__ double comp(int c) const { return c == moved ? val : st[(unsigned long long)c * stride]; }
+  __device__ __forceinline__ void store(int t, double v) const { if (tval) (direct ? tval : tcand)[(unsigned long long)t * tstride] = v; }
+  __device__ __forceinline__ double cached(int t) const { return tval[(unsigned long long)t * tstride]; }
 };
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------
@@ -161,6 +174,9 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
     ctx.consts = reinterpret_cast<const double*>(smem + m.off_consts);
     ctx.plates = reinterpret_cast<const amwg_plate*>(smem + m.off_plates);
     ctx.params = reinterpret_cast<const amwg_param*>(smem + m.off_params);
+    ctx.comp_prog = reinterpret_cast<const int*>(smem + m.off_comp_prog);
+    ctx.touch_off = reinterpret_cast<const int*>(smem + m.off_touch_off);
+    ctx.touch_terms = reinterpret_cast<const int*>(smem + m.off_touch_terms);
     for (int k = 0; k < m.n_columns; ++k) {
       bool in_smem = m.col_smem_off[k] >= 0;
       ctx.col[k] = in_smem ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
@@ -447,7 +463,8 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
     const unsigned w = (unsigned)AMWG_NEXT();
     const int op = w & 0xff;
     const bool acc = (w >> 16) & 1;
-    const int a = (int)(w >> 17);
+    const bool store = (w & AMWG_STORE_FLAG) != 0;
+    const int a = (int)(w >> 18);
     // operands, last one first (the order inline words are laid out and stack operands are popped)
     double x = 0.0, y = 0.0, z = 0.0, t = 0.0;
     if (op != AMWG_OP_PLATE) {                          // plates fetch their own operands
@@ -493,21 +510,32 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
       case AMWG_OP_UNIF_K: r = (x < y || x > z) ? -CUDART_INF : t; break;
       case AMWG_OP_BETA_K: r = (x > 1 || x < 0) ? -CUDART_INF : (y * js_log(x) + z * js_log(1 - x)) - t; break;
       case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
+      case AMWG_OP_ACC_RANGE: {              // terms that do not read the moved component: their cached values, one by one, in order
+        const int cnt = AMWG_NEXT();
+        for (int k = 0; k < cnt; ++k) lp = lp + es.cached(a + k);
+        has_r = false;
+        break;
+      }
       case AMWG_OP_PLATE: {
         has_r = false;
         const int kind = ctx.plates[a].kind;
+        double v = 0.0;
         if (kind == AMWG_PLATE_NORM_IID) {
           double mean, sd; AMWG_OPND(sd, (w >> 10) & 3); AMWG_OPND(mean, (w >> 8) & 3);
-          lp = lp + plate_norm_iid(ctx, a, mean, sd);
+          v = plate_norm_iid(ctx, a, mean, sd);
+          lp = lp + v;
         } else if (kind == AMWG_PLATE_BERN_IID) {
           double p; AMWG_OPND(p, (w >> 8) & 3);
           lp = plate_bern_iid(ctx, a, p, lp);
         } else if (kind == AMWG_PLATE_NORM_GROUPED) {
           double sd; AMWG_OPND(sd, (w >> 8) & 3);
-          lp = lp + plate_norm_grouped(ctx, a, es, sd);
+          v = plate_norm_grouped(ctx, a, es, sd);
+          lp = lp + v;
         } else if (kind == AMWG_PLATE_POIS_LOGLIN) {
-          lp = lp + plate_pois_loglin(ctx, a, es);
+          v = plate_pois_loglin(ctx, a, es);
+          lp = lp + v;
         }
+        if (store) { const int t = AMWG_NEXT(); es.store(t, v); }
         break;
       }
       case AMWG_OP_LOOP_BEGIN: {
@@ -530,8 +558,10 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
       default: r = cold_op(op, x, y, z, t); break;
     }
     if (has_r) {
-      if (acc) lp = lp + r;
-      else { stk[sp] = tos; ++sp; tos = r; }
+      if (acc) {
+        lp = lp + r;
+        if (store) { const int t = AMWG_NEXT(); es.store(t, r); }
+      } else { stk[sp] = tos; ++sp; tos = r; }
     }
   }
 #undef AMWG_NEXT
@@ -599,6 +629,7 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
   }
   // every chain starts from the same `init`: evaluate from it directly (a shadow thread must not race with the owner's writes)
   EvalState es{init, 1, -1, 0.0};
+  if (m.n_terms > 0 && valid) { es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = a.C; es.direct = true; }
   double lp0 = eval_logpost(ctx, es, logpost_pc(m, es));
   if (valid) a.curr_lp[chain] = lp0;
 }
@@ -702,7 +733,12 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         double lp_new = 0.0;
         if (need || ctx.ring_saddr) {                     // with the tile ring the plate is a CTA-wide collective: nobody may skip it
           EvalState es{st, C, c, need ? prop : cur};
-          lp_new = eval_logpost(ctx, es, logpost_pc(m, es));
+          int pc = logpost_pc(m, es);
+          if (m.n_terms > 0) {                            // dependency-aware: only the terms that read component c are recomputed
+            es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
+            pc = ctx.comp_prog[c];
+          }
+          lp_new = eval_logpost(ctx, es, pc);
         }
         // ---- phase 3: accept / reject
         if (sync) __syncthreads();
@@ -713,8 +749,14 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           double z0 = z0raw - mx, z1 = z1raw - mx;
           double zero_prob = js_exp(z0 - js_log(js_exp(z0) + js_exp(z1)));
           bool zero = g.next() < zero_prob;
+          const bool changed = zero != (cur == 0.0);
           if (valid) st[ci] = zero ? 0.0 : 1.0;
           curr = zero ? z0raw : z1raw;
+          if (changed && valid && m.n_terms > 0)
+            for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
+              const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
+              a.tval[ti] = a.tcand[ti];
+            }
         } else if (need) {
           // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
           double accept_prob = js_exp(lp_new - curr);
@@ -723,6 +765,11 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
             if (valid) {
               st[ci] = prop;
               if (m.adapting[c]) acc[ci] += 1;
+              if (m.n_terms > 0)                          // commit the recomputed terms to the chain's term cache
+                for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
+                  const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
+                  a.tval[ti] = a.tcand[ti];
+                }
             }
           }
         }
@@ -897,6 +944,16 @@ static int validate_model(const amwg_model* md) {
   for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v)
     if (md->variant_logpost[v] < 0 || md->variant_logpost[v] >= md->n_code) return fail("amwg_create: variant program out of range");
   if (md->n_derived > 0 && (md->derived_prog < 0 || md->derived_prog >= md->n_code)) return fail("amwg_create: derived_prog out of range");
+  if (md->comp_prog && md->n_terms > 0) {
+    if (!md->touch_off || !md->touch_terms) return fail("amwg_create: comp_prog without touch lists");
+    if (md->n_variant_comps > 0) return fail("amwg_create: comp_prog cannot be combined with variant programs");
+    for (int c = 0; c < md->n_comp; ++c) {
+      if (md->comp_prog[c] < 0 || md->comp_prog[c] >= md->n_code) return fail("amwg_create: comp_prog out of range");
+      if (md->touch_off[c] > md->touch_off[c + 1]) return fail("amwg_create: touch_off must be non-decreasing");
+    }
+    for (int k = 0; k < md->touch_off[md->n_comp]; ++k)
+      if (md->touch_terms[k] < 0 || md->touch_terms[k] >= md->n_terms) return fail("amwg_create: touch_terms out of range");
+  }
   for (int k = 0; k < md->n_fold; ++k)
     if (md->fold_prog[k] < 0 || md->fold_prog[k] >= md->n_code || md->fold_dst[k] < 0 || md->fold_dst[k] >= md->n_consts)
       return fail("amwg_create: constant-folding table out of range");
@@ -959,6 +1016,11 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   m.off_consts = append(md->consts, sizeof(double) * (size_t)md->n_consts);
   m.off_plates = append(md->plates, sizeof(amwg_plate) * (size_t)md->n_plates);
   m.off_params = append(md->params, sizeof(amwg_param) * (size_t)md->n_params);
+  m.n_terms = (md->comp_prog && md->n_terms > 0) ? md->n_terms : 0;
+  if (const char* e = getenv("AMWG_TERM_CACHE")) { if (atoi(e) == 0) m.n_terms = 0; }
+  m.off_comp_prog = append(md->comp_prog, m.n_terms ? sizeof(int32_t) * (size_t)md->n_comp : 0);
+  m.off_touch_off = append(md->touch_off, m.n_terms ? sizeof(int32_t) * (size_t)(md->n_comp + 1) : 0);
+  m.off_touch_terms = append(md->touch_terms, m.n_terms ? sizeof(int32_t) * (size_t)md->touch_off[md->n_comp] : 0);
   m.image_bytes = (unsigned)image.size();
   unsigned char* d_image = nullptr;
   if (dev_upload(s, image.data(), image.size(), &d_image)) return bail(-1);
@@ -1017,6 +1079,11 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   if (dev_alloc(s, DC, &a.state) || dev_alloc(s, DC, &a.pls) || dev_alloc(s, DC, &a.psd) || dev_alloc(s, DC, &a.acc) || dev_alloc(s, (size_t)n_chains, &a.curr_lp) ||
       dev_alloc(s, (size_t)n_chains, &a.perm) || dev_alloc(s, (size_t)n_chains, &a.rng_n))
     return bail(-1);
+  a.tval = a.tcand = nullptr;
+  if (m.n_terms > 0) {
+    if (dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tval) || dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tcand)) return bail(-1);
+    s->chains_per_thread = 1;            // the experimental wide kernel evaluates the full program only
+  }
 
   double* d_init = nullptr; double* d_pls0 = nullptr;
   std::vector<double> pls0(s->D);

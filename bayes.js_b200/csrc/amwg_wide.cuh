@@ -150,7 +150,8 @@ __device__ __noinline__ void run_logpost_w(unsigned code_sa, unsigned consts_sa,
     const unsigned w = (unsigned)WNEXT();
     const int op = w & 0xff;
     const bool acc = (w >> 16) & 1;
-    const int a = (int)(w >> 17);
+    const bool store = (w & AMWG_STORE_FLAG) != 0;      // term-cache ids in the full program are skipped: this variant does not cache
+    const int a = (int)(w >> 18);
     double x[W], y[W], z[W], t[W], r[W];
 #pragma unroll
     for (int k = 0; k < W; ++k) { x[k] = 0.0; y[k] = 0.0; z[k] = 0.0; t[k] = 0.0; r[k] = 0.0; }
@@ -226,6 +227,7 @@ __device__ __noinline__ void run_logpost_w(unsigned code_sa, unsigned consts_sa,
             lp[k] = lp[k] + plate_pois_loglin(ctx, a, e1);
           }
         }
+        if (store) (void)WNEXT();
         break;
       }
       case AMWG_OP_LOOP_BEGIN: {
@@ -254,6 +256,7 @@ __device__ __noinline__ void run_logpost_w(unsigned code_sa, unsigned consts_sa,
       if (acc) {
 #pragma unroll
         for (int k = 0; k < W; ++k) lp[k] = lp[k] + r[k];
+        if (store) (void)WNEXT();
       } else {
 #pragma unroll
         for (int k = 0; k < W; ++k) { stk[sp][k] = tos[k]; tos[k] = r[k]; }

@@ -394,6 +394,14 @@ class AmwgSampler(Sampler):
         m.n_fold = len(prog.fold_prog)
         m.fold_prog = fold_prog.ctypes.data_as(C.POINTER(C.c_int32))
         m.fold_dst = fold_dst.ctypes.data_as(C.POINTER(C.c_int32))
+        comp_prog = np.asarray(prog.comp_prog if prog.n_terms else [0], dtype=np.int32)
+        touch_off = np.asarray(prog.touch_off if prog.n_terms else [0], dtype=np.int32)
+        touch_terms = np.asarray(prog.touch_terms if prog.touch_terms else [0], dtype=np.int32)
+        m.n_terms = prog.n_terms
+        m.comp_prog = comp_prog.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
+        m.touch_off = touch_off.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
+        m.touch_terms = touch_terms.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
+        self._cache_keepalive = (comp_prog, touch_off, touch_terms)
         vcomps = np.asarray(prog.variant_comps if prog.variant_comps else [0], dtype=np.int32)
         vlp = np.asarray(prog.variant_logpost if prog.variant_logpost else [0], dtype=np.int32)
         vder = np.asarray(prog.variant_derived if prog.variant_derived else [-1], dtype=np.int32)

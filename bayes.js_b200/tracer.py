@@ -288,7 +288,8 @@ class DataObject(dict):
 # tracing + lowering
 # ------------------------------------------------------------------------------------------------
 _MIN_PLATE = 8          # shorter runs stay unrolled scalar terms
-MAX_IMMEDIATE = 32767
+MAX_IMMEDIATE = 16383
+STORE_FLAG = 1 << 17
 MODE_STACK, MODE_CONST, MODE_COMP, MODE_NONE = 0, 1, 2, 3
 _ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, "SQRT": 1, "ABS": 1, "POW": 2,
           "LT": 2, "LE": 2, "GT": 2, "GE": 2, "EQ": 2, "NE": 2, "AND": 2, "OR": 2, "NOT": 1, "SELECT": 3,
@@ -310,6 +311,10 @@ class Program:
         self.logpost_prog = 0
         self.derived_prog = -1
         self.derived_names: List[str] = []
+        self.n_terms = 0                       # dependency-aware evaluation (amwg.h comp_prog): 0 = not in use
+        self.comp_prog: List[int] = []
+        self.touch_off: List[int] = []
+        self.touch_terms: List[int] = []
         self.variant_comps: List[int] = []     # binary components whose configuration selects the program (amwg.h variant_*)
         self.variant_logpost: List[int] = []
         self.variant_derived: List[int] = []
@@ -330,14 +335,20 @@ class Program:
         self.consts.append(float("nan"))       # filled by amwg_fold_kernel at create
         return len(self.consts) - 1
 
-    def emit(self, op: str, operand: int = 0, *extra: int, modes=(), acc: bool = False):
-        """One instruction word (include/amwg.h): opcode | operand modes A..D | ACC flag | 15-bit immediate, + extra words."""
+    def emit(self, op: str, operand: int = 0, *extra: int, modes=(), acc: bool = False, store: Optional[int] = None):
+        """One instruction word (include/amwg.h): opcode | operand modes A..D | ACC | STORE | 14-bit immediate, + extra words
+        (`store`: term id, written last)."""
         operand = int(operand)
         if not 0 <= operand <= MAX_IMMEDIATE:
-            raise JsThrow("log_post is too large for the device program format (immediate > 32767)")
+            raise JsThrow("log_post is too large for the device program format (immediate > 16383)")
         m = list(modes) + [MODE_NONE] * (4 - len(modes))
-        self.code.append(OP[op] | (m[0] << 8) | (m[1] << 10) | (m[2] << 12) | (m[3] << 14) | ((1 if acc else 0) << 16) | (operand << 17))
+        word = OP[op] | (m[0] << 8) | (m[1] << 10) | (m[2] << 12) | (m[3] << 14) | ((1 if acc else 0) << 16) | (operand << 18)
+        if store is not None:
+            word |= STORE_FLAG
+        self.code.append(word)
         self.code.extend(int(e) for e in extra)
+        if store is not None:
+            self.code.append(int(store))
 
 
 class Tracer:
@@ -550,6 +561,9 @@ class Lowering:
         self.prog.columns = tracer.columns       # shared list: synthesized columns are appended
         self._fold_memo: Dict[tuple, int] = {}
         self._fold_trees: List[Tuple[int, Sym]] = []
+        self._terms: List[dict] = []             # top-level terms of the (single) log_post program: start, end, kind, deps, cost
+        self._abs_words: List[int] = []          # positions of words that hold absolute program offsets (loop targets)
+        self._record_terms = False
 
     # -- constant folding ---------------------------------------------------------------------------
     def _key(self, n: Sym):
@@ -603,32 +617,47 @@ class Lowering:
                 words.append(il[1])
         return modes, list(reversed(words))
 
-    def _emit(self, n: Sym, acc: bool):
+    def _emit(self, n: Sym, acc: bool, store: Optional[int] = None):
         p = self.prog
         if n.op in ("CONST", "FOLD", "COMP"):
             mode, idx = self._inline(n)
-            p.emit("CONST" if mode == MODE_CONST else "COMP", idx, acc=acc)
+            p.emit("CONST" if mode == MODE_CONST else "COMP", idx, acc=acc, store=store)
         elif n.op == "DATA":
-            p.emit("DATA", n.val[0], n.val[1], acc=acc)
+            p.emit("DATA", n.val[0], n.val[1], acc=acc, store=store)
         elif n.op == "DATA_I":
-            p.emit("DATA_I", n.val[0], n.val[1], n.val[2], acc=acc)
+            p.emit("DATA_I", n.val[0], n.val[1], n.val[2], acc=acc, store=store)
         elif n.op == "COMP_I":
-            p.emit("COMP_I", n.val[0], n.val[1], n.val[2], n.val[3], acc=acc)
+            p.emit("COMP_I", n.val[0], n.val[1], n.val[2], n.val[3], acc=acc, store=store)
         else:
             if n.op not in _ARITY:
                 raise JsThrow(f"cannot lower operation {n.op}")
             modes, words = self._operands(n.args)
-            p.emit(n.op, 0, *words, modes=modes, acc=acc)
+            p.emit(n.op, 0, *words, modes=modes, acc=acc, store=store)
 
-    def emit_expr(self, node: Sym, prepare: bool = True, acc: bool = False):
+    def emit_expr(self, node: Sym, prepare: bool = True, acc: bool = False, store: Optional[int] = None):
         """Postfix emission. `prepare`: expand LD_* into primitives and fold constants first. `acc`: the value is
-        added to lp (a term of the sum) instead of being left on the stack."""
+        added to lp (a term of the sum) instead of being left on the stack; `store`: ... and kept in the term cache as term `store`."""
         if prepare:
             node = self.fold(expand(node))
         import sys
         if sys.getrecursionlimit() < 20000:
             sys.setrecursionlimit(20000)
-        self._emit(node, acc)
+        self._emit(node, acc, store)
+
+    def _deps(self, node: Sym) -> set:
+        """state components an (expanded) expression reads"""
+        out, stack = set(), [node]
+        while stack:
+            n = stack.pop()
+            if n.op == "COMP":
+                out.add(n.val)
+            elif n.op == "COMP_I":
+                col, off, stride, base, pid = n.val
+                cnt = self.t.plate_sizes.get(pid, 0)
+                idx = self.t.columns[col][off: off + stride * max(cnt, 1): stride] if cnt else self.t.columns[col]
+                out.update(int(base + v) for v in np.unique(idx))
+            stack.extend(n.args)
+        return out
 
     def prepared(self, node: Sym) -> Sym:
         return self.fold(expand(node))
@@ -680,17 +709,32 @@ class Lowering:
                 pl["iparam"][0] = base; pl["iparam"][1] = K
                 p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
         p.plates.append(pl)
+        start = len(p.code)
         if pl["kind"] != PLATE_GENERIC:
-            modes, words = self._operands([self.prepared(o) for o in operands])
-            p.emit("PLATE", q, *words, modes=modes)
+            prepared = [self.prepared(o) for o in operands]
+            modes, words = self._operands(prepared)
+            value_plate = pl["kind"] != PLATE_BERN_IID              # the Bernoulli plate adds term by term into lp: not a separable value
+            tid = len(self._terms) if (self._record_terms and value_plate) else None
+            p.emit("PLATE", q, *words, modes=modes, store=tid)
+            if self._record_terms:
+                deps = set()
+                for o in prepared:
+                    deps |= self._deps(o)
+                if pl["kind"] == PLATE_NORM_GROUPED or pl["kind"] == PLATE_POIS_LOGLIN:
+                    deps |= set(range(pl["iparam"][0], pl["iparam"][0] + pl["iparam"][1]))
+                self._terms.append(dict(start=start, end=len(p.code), kind="value" if value_plate else "inorder", deps=deps, cost=3 * n))
             return
         # generic: a bytecode loop, lp += body(i) in order
         p.emit("LOOP_BEGIN", q, 0)
         fix = len(p.code) - 1
+        self._abs_words.append(fix)
         body_start = len(p.code)
         self.emit_expr(body)
         p.emit("LOOP_END", 0, body_start)
+        self._abs_words.append(len(p.code) - 1)
         p.code[fix] = len(p.code)
+        if self._record_terms:
+            self._terms.append(dict(start=start, end=len(p.code), kind="inorder", deps=set(), cost=12 * n * max(1, len(p.code) - body_start)))
         p.summary.append(f"plate GENERIC n={n} body={body.op}")
 
     def _grouped(self, mean: Sym, n: int):
@@ -742,7 +786,12 @@ class Lowering:
                 self._emit_plate(body, length)
                 i += length
                 continue
-            self.emit_expr(tm, acc=True)
+            node = self.prepared(tm)
+            start = len(p.code)
+            tid = len(self._terms) if self._record_terms else None
+            self.emit_expr(node, prepare=False, acc=True, store=tid)
+            if self._record_terms:
+                self._terms.append(dict(start=start, end=len(p.code), kind="value", deps=self._deps(node), cost=10 * (len(p.code) - start)))
             p.summary.append(f"term {tm.op}")
             i += 1
         p.emit("END")
@@ -769,8 +818,60 @@ class Lowering:
             p.emit("END")
         return p
 
+    def _emit_component_programs(self):
+        """Dependency-aware evaluation (amwg.h comp_prog): for every component c a program that recomputes only the terms that
+        read c and adds the others from the chain's term cache, each in its original position. Only worth it when it removes
+        a good part of the work (hierarchical models); models whose every step touches the big plate keep the full program."""
+        p, terms = self.prog, self._terms
+        value_ids = [t for t, tr in enumerate(terms) if tr["kind"] == "value"]
+        if not value_ids or len(terms) > MAX_IMMEDIATE:
+            return
+        full = sum(tr["cost"] for tr in terms)
+        per_comp = []
+        for c in range(self.n_comp):
+            per_comp.append(sum(tr["cost"] for tr in terms if tr["kind"] == "inorder" or c in tr["deps"]) +
+                            3 * sum(1 for tr in terms if tr["kind"] == "value" and c not in tr["deps"]) + 40)
+        if sum(per_comp) > 0.6 * full * self.n_comp:
+            return
+        abs_words = sorted(self._abs_words)
+        p.n_terms = len(terms)
+        for c in range(self.n_comp):
+            p.comp_prog.append(len(p.code))
+            p.touch_off.append(len(p.touch_terms))
+            run_start, run_len = None, 0
+
+            def flush():
+                nonlocal run_start, run_len
+                if run_len:
+                    p.emit("ACC_RANGE", run_start, run_len)
+                run_start, run_len = None, 0
+            for t, tr in enumerate(terms):
+                if tr["kind"] == "value" and c not in tr["deps"]:
+                    if run_len and run_start + run_len == t:
+                        run_len += 1
+                    else:
+                        flush()
+                        run_start, run_len = t, 1
+                    continue
+                flush()
+                delta = len(p.code) - tr["start"]
+                frag = list(p.code[tr["start"]:tr["end"]])
+                for pos in abs_words:
+                    if tr["start"] <= pos < tr["end"]:
+                        frag[pos - tr["start"]] += delta
+                p.code.extend(frag)
+                if tr["kind"] == "value":
+                    p.touch_terms.append(t)
+            flush()
+            p.emit("END")
+        p.touch_off.append(len(p.touch_terms))
+        p.summary.append(f"dependency-aware evaluation: {len(terms)} terms, cost {sum(per_comp) / (full * self.n_comp):.2f} of the full program")
+
     def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
+        self._record_terms = True
         self.prog.logpost_prog, self.prog.derived_prog = self.add_logpost(result, derived)
+        self._record_terms = False
+        self._emit_component_programs()
         return self.finish()
 
     def _find_run(self, terms: List[Sym], i0: int):

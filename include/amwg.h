@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 5
+#define AMWG_ABI_VERSION 6
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -73,7 +73,9 @@ typedef struct {
  *     bits 12-13  mode of operand C
  *     bits 14-15  mode of operand D
  *     bit  16     ACC flag: the result is added to lp (lp = lp + result) instead of being pushed
- *     bits 17-31  immediate `a` (const index, component, column, plate id ...)
+ *     bit  17     STORE flag (only with ACC, or on PLATE): the value is also written to the chain's term cache; the term id
+ *                 follows as the last extra word of the instruction
+ *     bits 18-31  immediate `a` (const index, component, column, plate id ...)
  * Inline operand words follow the instruction word in consumption order: last operand first (D, C, B, A), which is
  * also the order stack operands are popped.  Further extra words are noted per opcode.
  * The accumulator `lp` starts at 0 and receives terms strictly in program order, so the sum is formed in the same
@@ -87,8 +89,9 @@ typedef struct {
 #define AMWG_MODE_NONE 3
 #define AMWG_WORD(op, mA, mB, mC, mD, acc, a) \
   ((int32_t)((uint32_t)(op) | ((uint32_t)(mA) << 8) | ((uint32_t)(mB) << 10) | ((uint32_t)(mC) << 12) | ((uint32_t)(mD) << 14) | \
-             ((uint32_t)((acc) ? 1 : 0) << 16) | ((uint32_t)(a) << 17)))
-#define AMWG_MAX_IMMEDIATE 32767
+             ((uint32_t)((acc) ? 1 : 0) << 16) | ((uint32_t)(a) << 18)))
+#define AMWG_STORE_FLAG (1u << 17)
+#define AMWG_MAX_IMMEDIATE 16383
 
 enum {
   AMWG_OP_END = 0,
@@ -117,6 +120,8 @@ enum {
   AMWG_OP_NORM_K,       /* (x, mean, K1, K2): K1 - pow(x-mean,2)/K2,  K1 = -0.5*log(2pi) - log(sd), K2 = 2*sd*sd   (:119-121) */
   AMWG_OP_UNIF_K,       /* (x, min, max, K):  (x<min || x>max) ? -inf : K,  K = log(1/(max-min))                    (:221-223) */
   AMWG_OP_BETA_K,       /* (x, a1, b1, K):    (x>1 || x<0) ? -inf : a1*log(x) + b1*log(1-x) - K, a1 = shape1-1, b1 = shape2-1, K = lbeta (:104-113) */
+  AMWG_OP_ACC_RANGE,    /* lp = lp + cache[a] + cache[a+1] + ... (next word: count), one term at a time, in order: the terms of the
+                           sum that do not read the moved component, taken from the chain's term cache (see amwg_model.comp_prog) */
   AMWG_OP__COUNT
 };
 
@@ -162,6 +167,14 @@ typedef struct {
    * expression, so the host records log_post once per configuration of up to AMWG_MAX_VARIANT_COMPS binary components.
    * Configuration v has bit k set when state component variant_comps[k] is non-zero (the proposal counts for the moved one);
    * its programs start at variant_logpost[v] / variant_derived[v]. n_variant_comps == 0: logpost_prog / derived_prog are used. */
+  /* Dependency-aware evaluation (optional). log_post is a sum of terms; a step that moves component c only changes the terms
+   * that read c. With comp_prog != NULL the sampler keeps every value-term of every chain in a term cache (n_terms doubles per
+   * chain) and evaluates a proposal for component c with comp_prog[c]: the terms that read c are recomputed (STORE flag: the new
+   * value goes to a candidate slot), the others are added from the cache by ACC_RANGE -- each in its original position, so the
+   * sum is formed in the same order with the same values as the full program (bit-identical). On acceptance the candidates of
+   * touch_terms[touch_off[c] .. touch_off[c+1]) are committed. logpost_prog is the full program (it stores every value-term). */
+  int32_t n_terms;          const int32_t* comp_prog;      /* n_comp word offsets, or NULL */
+  const int32_t* touch_off; const int32_t* touch_terms;    /* n_comp + 1 offsets into touch_terms */
   int32_t n_variant_comps;  const int32_t* variant_comps;
   const int32_t* variant_logpost;  const int32_t* variant_derived;     /* 1 << n_variant_comps entries each (derived: -1 if none) */
 } amwg_model;

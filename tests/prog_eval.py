@@ -23,7 +23,9 @@ def fold_constants(prog, O):
     return consts
 
 
-def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0):
+def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0, cache=None, cand=None):
+    """`cache` / `cand`: the chain's term cache (list of n_terms values) and where STORE writes (cand, or the cache itself when
+    cand is None) -- mirrors EvalState.tval / tcand / direct."""
     code, cols, plates = prog.code, prog.columns, prog.plates
     stk = []
     lp = 0.0
@@ -61,8 +63,9 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
         w = nxt() & 0xffffffff
         op = INV[w & 0xff]
         mA, mB, mC, mD = (w >> 8) & 3, (w >> 10) & 3, (w >> 12) & 3, (w >> 14) & 3
-        acc, a = (w >> 16) & 1, w >> 17
+        acc, store, a = (w >> 16) & 1, (w >> 17) & 1, w >> 18
         r = None
+        plate_v = None
         if op == "END":
             return stk[-1] if (want_top and stk) else lp
         if op == "CONST": r = consts[a]
@@ -92,6 +95,10 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
             args = [opnd(m) for m in (mA, mB, mC, mD)[:n][::-1]][::-1]
             r = _ld(O, op[3:].lower(), *args)
         elif op == "ACC": lp = lp + stk.pop()
+        elif op == "ACC_RANGE":
+            cnt = nxt()
+            for k in range(cnt):
+                lp = lp + cache[a + k]
         elif op == "STORE": der[a] = stk.pop()
         elif op == "LOOP_BEGIN":
             skip = nxt()
@@ -110,7 +117,8 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
             if pl["kind"] == PLATE_NORM_IID:
                 sd = opnd(mB); mean = opnd(mA)
                 S = float(np.sum((x - mean) ** 2))
-                lp = lp + (n * (c0 - O.orc_log(sd)) - S / (2 * sd * sd))
+                plate_v = n * (c0 - O.orc_log(sd)) - S / (2 * sd * sd)
+                lp = lp + plate_v
             elif pl["kind"] == PLATE_BERN_IID:
                 p = opnd(mA)
                 l1 = O.orc_log(1.0 * p + (1 - 1.0) * (1 - p)); l0 = O.orc_log(0.0 * p + (1 - 0.0) * (1 - p))
@@ -122,20 +130,31 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0)
                 S = 0.0
                 for j in range(J):
                     S += float(np.sum((x[start[j]:start[j + 1]] - comp(base + j)) ** 2))
-                lp = lp + (n * (c0 - O.orc_log(sd)) - S / (2 * sd * sd))
+                plate_v = n * (c0 - O.orc_log(sd)) - S / (2 * sd * sd)
+                lp = lp + plate_v
             elif pl["kind"] == PLATE_POIS_LOGLIN:
                 base, K = pl["iparam"][0], pl["iparam"][1]
                 X = np.asarray(cols[pl["col"][1]]).reshape(-1, K)[:n]
                 lf = np.asarray(cols[pl["col"][2]])[:n]
                 beta = np.array([comp(base + k) for k in range(K)])
                 eta = X @ beta
-                lp = lp + float(np.sum(x * eta - np.exp(eta) - lf))
+                plate_v = float(np.sum(x * eta - np.exp(eta) - lf))
+                lp = lp + plate_v
             else:
                 raise AssertionError("generic plates are LOOP_BEGIN/LOOP_END")
+            if store:
+                t_id = nxt()
+                if cache is not None:
+                    (cand if cand is not None else cache)[t_id] = plate_v if plate_v is not None else 0.0
         else:
             raise AssertionError(op)
         if r is not None:
-            if acc: lp = lp + r
+            if acc:
+                lp = lp + r
+                if store:
+                    t_id = nxt()
+                    if cache is not None:
+                        (cand if cand is not None else cache)[t_id] = r
             else: stk.append(r)
 
 

@@ -129,11 +129,31 @@ def test_hierarchical_and_regression_plates(pkg, orc):
     params = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
     prog, _, n = _trace(pkg, hier, params, {"y": y.tolist(), "g": g.tolist()})
     assert n == J + 1
-    assert prog.summary[-J:] == [f"plate NORM_IID n={per}"] * J         # one plate per group: mu_j only touches its own
+    plates = [x for x in prog.summary if x.startswith("plate")]
+    assert plates == [f"plate NORM_IID n={per}"] * J                    # one plate per group: mu_j only touches its own
     consts = prog_eval.fold_constants(prog, orc.lib())
     st = list(rng.normal(100, 20, J)) + [4.0]
     ref, _ = _oracle_logpost(orc, "hier_norm", {"y": y, "g": g}, params, st)
     assert abs(prog_eval.logpost(prog, consts, st, orc.lib()) - ref) <= 1e-12 * abs(ref)
+    # dependency-aware evaluation: a step on mu_j recomputes its prior and its group's plate only; the other terms come from the
+    # chain's term cache, in their original positions -> the same sum, bit for bit, as the full program
+    assert prog.n_terms == 2 * J + 1 and len(prog.comp_prog) == J + 1
+    assert [prog.touch_off[c + 1] - prog.touch_off[c] for c in range(J + 1)] == [2] * J + [J + 1]
+    O = orc.lib()
+    cache = [None] * prog.n_terms
+    full0 = prog_eval.run(prog, consts, st, prog.logpost_prog, O, cache=cache)            # initial full evaluation fills the cache
+    assert None not in cache and full0 == prog_eval.logpost(prog, consts, st, O)
+    for step in range(60):
+        c = int(rng.integers(0, J + 1))
+        v = st[c] + rng.normal(0, 0.5) if c < J else abs(st[c] + rng.normal(0, 0.3))
+        cand = list(cache)
+        fast = prog_eval.run(prog, consts, st, prog.comp_prog[c], O, moved=c, val=v, cache=cache, cand=cand)
+        slow = prog_eval.logpost(prog, consts, st, O, moved=c, val=v)
+        assert fast == slow, (step, c)
+        if rng.random() < 0.5:                                           # accept: commit the touched terms
+            st[c] = v
+            for k in range(prog.touch_off[c], prog.touch_off[c + 1]):
+                cache[prog.touch_terms[k]] = cand[prog.touch_terms[k]]
 
     K, n_pts = 3, 40
     X = np.column_stack([np.ones(n_pts), rng.normal(0, 0.5, (n_pts, K - 1))])
