@@ -311,6 +311,7 @@ class Program:
         self.logpost_prog = 0
         self.derived_prog = -1
         self.derived_names: List[str] = []
+        self.store_sites: List[Tuple[int, int]] = []
         self.n_terms = 0                       # dependency-aware evaluation (amwg.h comp_prog): 0 = not in use
         self.comp_prog: List[int] = []
         self.touch_off: List[int] = []
@@ -348,6 +349,7 @@ class Program:
         self.code.append(word)
         self.code.extend(int(e) for e in extra)
         if store is not None:
+            self.store_sites.append((len(self.code) - 1 - len(extra), len(self.code)))    # (flagged word, its term-id word)
             self.code.append(int(store))
 
 
@@ -823,16 +825,8 @@ class Lowering:
         read c and adds the others from the chain's term cache, each in its original position. Only worth it when it removes
         a good part of the work (hierarchical models); models whose every step touches the big plate keep the full program."""
         p, terms = self.prog, self._terms
-        value_ids = [t for t, tr in enumerate(terms) if tr["kind"] == "value"]
-        if not value_ids or len(terms) > MAX_IMMEDIATE:
-            return
         full = sum(tr["cost"] for tr in terms)
-        per_comp = []
-        for c in range(self.n_comp):
-            per_comp.append(sum(tr["cost"] for tr in terms if tr["kind"] == "inorder" or c in tr["deps"]) +
-                            3 * sum(1 for tr in terms if tr["kind"] == "value" and c not in tr["deps"]) + 40)
-        if sum(per_comp) > 0.6 * full * self.n_comp:
-            return
+        per_comp = self._per_component_cost()
         abs_words = sorted(self._abs_words)
         p.n_terms = len(terms)
         for c in range(self.n_comp):
@@ -867,11 +861,46 @@ class Lowering:
         p.touch_off.append(len(p.touch_terms))
         p.summary.append(f"dependency-aware evaluation: {len(terms)} terms, cost {sum(per_comp) / (full * self.n_comp):.2f} of the full program")
 
+    def _per_component_cost(self) -> List[int]:
+        terms = self._terms
+        return [sum(tr["cost"] for tr in terms if tr["kind"] == "inorder" or c in tr["deps"]) +
+                3 * sum(1 for tr in terms if tr["kind"] == "value" and c not in tr["deps"]) + 40 for c in range(self.n_comp)]
+
+    def _cache_worthwhile(self) -> bool:
+        terms = self._terms
+        if not any(tr["kind"] == "value" for tr in terms) or len(terms) > MAX_IMMEDIATE:
+            return False
+        full = sum(tr["cost"] for tr in terms)
+        return sum(self._per_component_cost()) <= 0.6 * full * self.n_comp
+
+    def _strip_stores(self, der_off: int) -> int:
+        """The model keeps the full program for every step: remove the term-cache stores again (flag + term-id word), so that the
+        hot program is exactly what it was without the feature. Returns the moved offset of the derived program."""
+        p = self.prog
+        removed = sorted(idw for _, idw in p.store_sites)
+        for flagged, _ in p.store_sites:
+            p.code[flagged] &= ~STORE_FLAG
+
+        def shift(off: int) -> int:
+            import bisect
+            return off - bisect.bisect_left(removed, off)
+        for pos in self._abs_words:
+            p.code[pos] = shift(p.code[pos])
+        self._abs_words = [shift(pos) for pos in self._abs_words]
+        for idw in reversed(removed):
+            del p.code[idw]
+        p.store_sites = []
+        return shift(der_off) if der_off >= 0 else der_off
+
     def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
         self._record_terms = True
-        self.prog.logpost_prog, self.prog.derived_prog = self.add_logpost(result, derived)
+        lp_off, der_off = self.add_logpost(result, derived)
         self._record_terms = False
-        self._emit_component_programs()
+        if self._cache_worthwhile():
+            self._emit_component_programs()
+        else:
+            der_off = self._strip_stores(der_off)
+        self.prog.logpost_prog, self.prog.derived_prog = lp_off, der_off
         return self.finish()
 
     def _find_run(self, terms: List[Sym], i0: int):
