@@ -112,19 +112,34 @@ struct Ctx {                       // lives in shared memory
   unsigned long long ring_bar[kRingStages];
 };
 
-struct EvalState {
+struct EvalStateBase {
   const double* st;   // state base + chain
   unsigned long long stride;
   int moved;          // component carrying the proposal, or -1
   double val;
+  __device__ __forceinline__ EvalStateBase(const double* st_, unsigned long long stride_, int moved_, double val_)
+      : st(st_), stride(stride_), moved(moved_), val(val_) {}
+  __device__ __forceinline__ double comp(int c) const { return c == moved ? val : st[(unsigned long long)c * stride]; }
+};
+// CACHE = false: the model evaluates the full program at every step (no term cache; the hot configuration of the headline
+// benchmark) -- the cache plumbing compiles away. CACHE = true: dependency-aware evaluation (amwg_model.comp_prog).
+template <bool CACHE>
+struct EvalStateT : EvalStateBase {
+  using EvalStateBase::EvalStateBase;
+  __device__ __forceinline__ void store(int, double) const {}
+  __device__ __forceinline__ double cached(int) const { return 0.0; }
+};
+template <>
+struct EvalStateT<true> : EvalStateBase {
+  using EvalStateBase::EvalStateBase;
   double* tval = nullptr;     // term cache of this chain (base + chain), stride tstride; nullptr: not in use
   double* tcand = nullptr;
   unsigned long long tstride = 0;
   bool direct = false;        // STORE writes the cache itself (initial full evaluation) instead of the candidate slots
-  __device__ __forceinline__ double comp(int c) const { return c == moved ? val : st[(unsigned long long)c * stride]; }
   __device__ __forceinline__ void store(int t, double v) const { if (tval) (direct ? tval : tcand)[(unsigned long long)t * tstride] = v; }
   __device__ __forceinline__ double cached(int t) const { return tval[(unsigned long long)t * tstride]; }
 };
+using EvalState = EvalStateT<true>;
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -334,7 +349,7 @@ __device__ __noinline__ double plate_bern_iid(const Ctx& ctx, int q, double p, d
 }
 
 // sum_i ld.norm(y_i, mu[g_i], sd) with points sorted by group; group j occupies [start[j], start[j+1]).
-__device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const EvalState& es, double sd) {
+__device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const EvalStateBase& es, double sd) {
   const amwg_plate& pl = ctx.plates[q];
   int c = pl.col[0], off = pl.iparam[2];
   const double* __restrict__ start = ctx.col[pl.col[1]];
@@ -363,7 +378,7 @@ __device__ __forceinline__ void pois_rows(const double* __restrict__ X, const do
   }
 }
 
-__device__ __noinline__ double plate_pois_loglin(const Ctx& ctx_in, int q, const EvalState& es) {
+__device__ __noinline__ double plate_pois_loglin(const Ctx& ctx_in, int q, const EvalStateBase& es) {
   Ctx& ctx = const_cast<Ctx&>(ctx_in);
   const amwg_plate& pl = ctx.plates[q];
   const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
@@ -445,8 +460,9 @@ __device__ __noinline__ double cold_op(int op, double x, double y, double z, dou
   }
 }
 
-__device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalState& es, int pc,
-                                           double* der, bool want_top) {
+template <bool CACHE>
+__device__ __noinline__ double run_program_t(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalStateT<CACHE>& es, int pc,
+                                             double* der, bool want_top) {
   double stk[kStack];
   double tos = 0.0;
   int sp = 0;
@@ -570,19 +586,23 @@ __device__ __noinline__ double run_program(unsigned code_sa, unsigned consts_sa,
 }
 
 // which recorded configuration of the binary components applies to this evaluation state (0 when the model has one program)
-__device__ __forceinline__ int variant_of(const ModelDev& m, const EvalState& es) {
+__device__ __forceinline__ double run_program(unsigned code_sa, unsigned consts_sa, const Ctx& ctx, const EvalState& es, int pc, double* der, bool want_top) {
+  return run_program_t<true>(code_sa, consts_sa, ctx, es, pc, der, want_top);
+}
+__device__ __forceinline__ int variant_of(const ModelDev& m, const EvalStateBase& es) {
   int v = 0;
   for (int k = 0; k < m.n_variant_comps; ++k) v |= (es.comp(m.variant_comps[k]) != 0.0) ? (1 << k) : 0;
   return v;
 }
-__device__ __forceinline__ int logpost_pc(const ModelDev& m, const EvalState& es) {
+__device__ __forceinline__ int logpost_pc(const ModelDev& m, const EvalStateBase& es) {
   return m.n_variant_comps ? m.variant_logpost[variant_of(m, es)] : m.logpost_prog;
 }
-__device__ __forceinline__ int derived_pc(const ModelDev& m, const EvalState& es) {
+__device__ __forceinline__ int derived_pc(const ModelDev& m, const EvalStateBase& es) {
   return m.n_variant_comps ? m.variant_derived[variant_of(m, es)] : m.derived_prog;
 }
-__device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalState& es, int pc) {
-  return run_program(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, nullptr, false);
+template <bool CACHE>
+__device__ __forceinline__ double eval_logpost(const Ctx& ctx, const EvalStateT<CACHE>& es, int pc) {
+  return run_program_t<CACHE>(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, nullptr, false);
 }
 __device__ __forceinline__ double run_ctx(const Ctx& ctx, const EvalState& es, int pc, double* der, bool want_top) {
   return run_program(smem_u32(ctx.code), smem_u32(ctx.consts), ctx, es, pc, der, want_top);
@@ -643,6 +663,7 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
 #ifndef AMWG_MINBLOCKS
 #define AMWG_MINBLOCKS 7
 #endif
+template <bool CACHE>
 __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ Ctx ctx;
@@ -732,13 +753,15 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         if (sync) __syncthreads(); else __syncwarp(__activemask());
         double lp_new = 0.0;
         if (need || ctx.ring_saddr) {                     // with the tile ring the plate is a CTA-wide collective: nobody may skip it
-          EvalState es{st, C, c, need ? prop : cur};
-          int pc = logpost_pc(m, es);
-          if (m.n_terms > 0) {                            // dependency-aware: only the terms that read component c are recomputed
+          EvalStateT<CACHE> es{st, C, c, need ? prop : cur};
+          int pc;
+          if constexpr (CACHE) {                          // dependency-aware: only the terms that read component c are recomputed
             es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
             pc = ctx.comp_prog[c];
+          } else {
+            pc = logpost_pc(m, es);
           }
-          lp_new = eval_logpost(ctx, es, pc);
+          lp_new = eval_logpost<CACHE>(ctx, es, pc);
         }
         // ---- phase 3: accept / reject
         if (sync) __syncthreads();
@@ -752,7 +775,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           const bool changed = zero != (cur == 0.0);
           if (valid) st[ci] = zero ? 0.0 : 1.0;
           curr = zero ? z0raw : z1raw;
-          if (changed && valid && m.n_terms > 0)
+          if (CACHE && changed && valid)
             for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
               const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
               a.tval[ti] = a.tcand[ti];
@@ -765,7 +788,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
             if (valid) {
               st[ci] = prop;
               if (m.adapting[c]) acc[ci] += 1;
-              if (m.n_terms > 0)                          // commit the recomputed terms to the chain's term cache
+              if (CACHE)                                  // commit the recomputed terms to the chain's term cache
                 for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
                   const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
                   a.tval[ti] = a.tcand[ti];
@@ -1064,7 +1087,8 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   if (const char* e = getenv("AMWG_CHAINS_PER_THREAD")) { int w = atoi(e); if (w == 1 || w == 2 || w == 4) s->chains_per_thread = w; }
   if (cudaFuncSetAttribute(amwg_sweep_kernel_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_sweep_kernel_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
-      cudaFuncSetAttribute(amwg_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
@@ -1135,7 +1159,8 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       amwg_sweep_kernel_wide<4><<<grid_for((C + 3) / 4, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
     } else {
       const int threads = s->m.phase_sync ? kSyncThreads : kThreads;
-      amwg_sweep_kernel<<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+      if (s->m.n_terms > 0) amwg_sweep_kernel<true><<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+      else amwg_sweep_kernel<false><<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
     }
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].second, s->stream));

@@ -406,8 +406,8 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
           } else {                                   // program depends on each chain's binary configuration: evaluate chain by chain
 #pragma unroll
             for (int k = 0; k < W; ++k) {
-              EvalState e1{es.st[k], C, es.moved[k], es.val[k]};
-              lp_new[k] = eval_logpost(ctx, e1, logpost_pc(m, e1));
+              EvalStateT<false> e1{es.st[k], C, es.moved[k], es.val[k]};
+              lp_new[k] = eval_logpost<false>(ctx, e1, logpost_pc(m, e1));
             }
           }
         }
