@@ -94,10 +94,10 @@ def hier(state, d):
 
 P4 = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
 t0 = time.perf_counter()
-s = mcmc.AmwgSampler(P4, hier, {"y": yy.tolist(), "g": g.tolist()}, {"chains": 1 << 14, "seed": 0})
+s = mcmc.AmwgSampler(P4, hier, {"y": yy.tolist(), "g": g.tolist()}, {"chains": 1 << 16, "seed": 0})
 t_trace = time.perf_counter() - t0
 r, ms = gpu_rate(s, 2, 4, reps=2)
-emit(config=4, what="GPU, hierarchical Normal N=65536, D=65, 2^14 chains on one GPU; dependency-aware evaluation (a mu_j step recomputes "
+emit(config=4, what="GPU, hierarchical Normal N=65536, D=65, 2^16 chains on one GPU (the BASELINE per-GPU share); dependency-aware evaluation (a mu_j step recomputes "
      "prior_j and group j's plate only: 131072 point-terms per draw instead of 65 x 65536), y read through L2", draws_per_s=r,
      trace_seconds=t_trace, n_plates=len(s._program.plates), program=s.program_summary()[-1])
 del s
