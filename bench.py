@@ -33,7 +33,8 @@ BURN = 1000                      # setup (untimed): BASELINE throughput run burn
 FLOP_PER_DRAW = 6144.0           # 2 components x 1024 points x 3 flop
 HBM_BYTES_PER_DRAW = 17.4        # 16 B sample write + ~1.4 B amortised state/log-SD/counters
 FP64_NOMINAL_TFLOPS = 37.0       # B200 non-tensor fp64 (HGX B200 datasheet: 296 TF / 8 GPUs); no measured figure in MEASURED_PEAKS.json
-NCU_DRAM_BYTES_PER_LAUNCH = 9.85e8   # ncu --set full, one amwg_sweep_kernel launch (50 sweeps, 2^20 chains): 0.894 GB written + 0.091 GB read
+NCU_DRAM_BYTES_PER_LAUNCH = 1.66e9   # ncu --set full (profiles/r01g), one amwg_sweep_kernel launch (50 sweeps, 2^20 chains): 1.589 GB written
+                                     # (0.84 GB of samples + local-memory spill traffic at the 72-register cap) + 0.071 GB read
 METRIC = "posterior draws/sec (chains x iters) Normal(mu,sigma) N=1024 at 1/2/4/8 B200"
 PARAMS = {"mu": {"type": "real"}, "sigma": {"type": "real", "lower": 0}}
 
@@ -233,7 +234,7 @@ def run_ours(args):
                        "l2": "every step writes its samples (iters*2*chains*8 B = %.2f GB > 126 MB L2), which flushes L2" % (iters * 2 * local * 8 / 1e9)},
             "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (iters % 50 == 0 and local == CHAINS_PER_GPU) else None,
-                         "traffic_source": "profiles/r01d: dram__bytes_read.sum + dram__bytes_write.sum of one 50-sweep launch over 2^20 chains",
+                         "traffic_source": "profiles/r01g: dram__bytes_read.sum + dram__bytes_write.sum of one 50-sweep launch over 2^20 chains",
                          "algorithmic_bytes_per_launch": HBM_BYTES_PER_DRAW * 50 * local,
                          "peak_source": how, "algorithmic_bytes_per_draw": HBM_BYTES_PER_DRAW,
                          "note": "north_star names HBM; with the N-point sum fused in-kernel the binding roof is the fp64 pipe, see roofline_fp64"},

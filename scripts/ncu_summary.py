@@ -57,10 +57,14 @@ def main():
     lines += ["", "Executed instruction mix: " + ", ".join(f"{k} {v / max(sum(ex), 1):.1%}" for k, v in top)]
     if so:
         elf = run(["cuobjdump", "-elf", so])
-        kern = m.get("Kernel Name", ("", ""))[1].split("(")[0].split("::")[-1]
+        kern = m.get("Kernel Name", ("", ""))[1].split("(")[0].split("::")[-1].replace("void ", "").strip()
+        targ = ""
+        if "<" in kern:                                   # template instantiation, e.g. amwg_sweep_kernel<0> -> ...kernelILb0EE
+            kern, arg = kern.split("<", 1)
+            targ = "ILb" + arg.rstrip(">").strip() + "E"
         funcs = []
         for ln in elf.splitlines():
-            mm = re.match(r"\s+0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+\S+\s+\$_ZN4amwg" + str(len(kern)) + kern + r"E[^$]*\$(\S+)", ln)
+            mm = re.match(r"\s+0x[0-9a-f]+\s+(0x[0-9a-f]+)\s+(0x[0-9a-f]+)\s+0x2\s+\S+\s+\S+\s+\$_ZN4amwg" + str(len(kern)) + kern + targ + r"E[^$]*\$(\S+)", ln)
             if mm:
                 funcs.append((int(mm.group(1), 16) // 16, int(mm.group(2), 16) // 16, mm.group(3)))
         funcs.sort()
