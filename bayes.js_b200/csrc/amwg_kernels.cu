@@ -677,11 +677,10 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
   if (!valid && !sync) return;
   const unsigned long long chain = valid ? tid : C - 1;
   double* st = a.state + chain;
-  const double* psd = a.psd + chain;
-  int* acc = a.acc + chain;
+  const unsigned long long gchain = a.first_chain + chain;      // global chain id: the Philox counter's upper words
 
   RandomStream g;
-  g.init(a.seed, a.first_chain + chain, a.rng_n[chain]);
+  g.init(a.rng_n[chain]);
   unsigned long long perm = a.perm[chain];
   double curr = a.curr_lp[chain];
   const int P = m.n_params;
@@ -714,20 +713,20 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
     }
     // -- AmwgStepper.step: shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
     for (int i = P - 1; i > 0; --i) {
-      int j = (int)floor(g.next() * (i + 1));
+      int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
       unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
       perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
       perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
     }
     for (int slot = 0; slot < P; ++slot) {
-      const amwg_param pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];
+      const amwg_param& pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];   // read from shared memory where needed: not kept in registers
       const int n_rounds = pa.n_comp;
       const int inner = pa.n_comp / pa.dim0;
       if (pa.n_comp > 1) {
         // nested_array_random_apply: fresh identity, shuffled, top level only (mcmc.js:246-252)
         for (int i = 0; i < pa.dim0; ++i) order[i] = (unsigned char)i;
         for (int i = pa.dim0 - 1; i > 0; --i) {
-          int j = (int)floor(g.next() * (i + 1));
+          int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
           unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
         }
       }
@@ -745,7 +744,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           need = true;
         } else {
           // generate_proposal (mcmc.js:519, 577-579 / 596-598) and the bounds check (:520)
-          prop = js_rnorm(g, cur, psd[ci]);
+          prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci + chain]);
           if (pa.type == AMWG_INT) prop = js_round(prop);
           need = !(prop < pa.lower || prop > pa.upper);
         }
@@ -771,7 +770,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           double mx = js_max(z0raw, z1raw);
           double z0 = z0raw - mx, z1 = z1raw - mx;
           double zero_prob = js_exp(z0 - js_log(js_exp(z0) + js_exp(z1)));
-          bool zero = g.next() < zero_prob;
+          bool zero = g.next(a.seed, gchain) < zero_prob;
           const bool changed = zero != (cur == 0.0);
           if (valid) st[ci] = zero ? 0.0 : 1.0;
           curr = zero ? z0raw : z1raw;
@@ -783,11 +782,11 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         } else if (need) {
           // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
           double accept_prob = js_exp(lp_new - curr);
-          if (accept_prob > g.next()) {
+          if (accept_prob > g.next(a.seed, gchain)) {
             curr = lp_new;
             if (valid) {
               st[ci] = prop;
-              if (m.adapting[c]) acc[ci] += 1;
+              if (m.adapting[c]) a.acc[ci + chain] += 1;
               if (CACHE)                                  // commit the recomputed terms to the chain's term cache
                 for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
                   const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
@@ -875,9 +874,9 @@ __global__ void amwg_primitive_kernel(int kind, const double* __restrict__ x, lo
   if (i >= n) return;
   if (kind == 0) out[i] = js_log(x[i]);
   else if (kind == 1) out[i] = js_exp(x[i]);
-  else if (kind == 2) { RandomStream g; g.init(seed, chain, (unsigned long long)i); out[i] = g.next(); }
+  else if (kind == 2) { RandomStream g; g.init((unsigned long long)i); out[i] = g.next(seed, chain); }
   else if (kind == 3) {   // sequential rnorm(x[0], x[1]) draws of one chain: thread 0 only
-    if (i == 0) { RandomStream g; g.init(seed, chain, 0); for (long long k = 0; k < n; ++k) out[k] = js_rnorm(g, x[0], x[1]); }
+    if (i == 0) { RandomStream g; g.init(0); for (long long k = 0; k < n; ++k) out[k] = js_rnorm(g, seed, chain, x[0], x[1]); }
   } else if (kind == 4) out[i] = js_round(x[i]);
 }
 

@@ -149,35 +149,33 @@ __device__ __noinline__ double2 philox_uniform_pair(uint32_t blk_lo, uint32_t bl
 // different positions (rnorm consumes a data-dependent number of uniforms), so the block is fetched at ONE call site per
 // draw with a per-lane block index: divergence in stream position never multiplies the Philox work.
 struct RandomStream {
-  uint32_t k0, k1, g0, g1;
+  // The key (seed) and the chain id are not stored: they live in the kernel's parameters / the thread's chain index, and
+  // every register kept alive across the log_post evaluation is one more spill at the sweep kernel's register cap.
   uint64_t n;          // index of the next Math.random() call of this chain
   uint64_t cb;         // index of the cached block (uniforms #2*cb, #2*cb+1), ~0 if none
   double c0, c1;
 
-  __device__ __forceinline__ void init(uint64_t seed, uint64_t chain, uint64_t pos) {
-    k0 = (uint32_t)seed; k1 = (uint32_t)(seed >> 32); g0 = (uint32_t)chain; g1 = (uint32_t)(chain >> 32);
-    n = pos; cb = ~0ull; c0 = c1 = 0.0;
-  }
-  __device__ __forceinline__ void load(uint64_t blk) {
-    double2 p = philox_uniform_pair((uint32_t)blk, (uint32_t)(blk >> 32), g0, g1, k0, k1);
+  __device__ __forceinline__ void init(uint64_t pos) { n = pos; cb = ~0ull; c0 = c1 = 0.0; }
+  __device__ __forceinline__ void load(uint64_t seed, uint64_t chain, uint64_t blk) {
+    double2 p = philox_uniform_pair((uint32_t)blk, (uint32_t)(blk >> 32), (uint32_t)chain, (uint32_t)(chain >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
     cb = blk; c0 = p.x; c1 = p.y;
   }
   // one uniform
-  __device__ __forceinline__ double next() {
+  __device__ __forceinline__ double next(uint64_t seed, uint64_t chain) {
     uint64_t blk = n >> 1;
-    if (cb != blk) load(blk);
+    if (cb != blk) load(seed, chain, blk);
     double u = (n & 1) ? c1 : c0;
     ++n;
     return u;
   }
   // two consecutive uniforms (#n, #n+1) with exactly one block fetch: for odd n the first one is the cached block's
   // second word and the new block provides the second one.
-  __device__ __forceinline__ void next2(double& u, double& v) {
-    if ((n & 1) && cb != (n >> 1)) load(n >> 1);          // only right after a kernel (re)start
+  __device__ __forceinline__ void next2(uint64_t seed, uint64_t chain, double& u, double& v) {
+    if ((n & 1) && cb != (n >> 1)) load(seed, chain, n >> 1);          // only right after a kernel (re)start
     double first_odd = c1;
     uint64_t blk = (n + 1) >> 1;                          // even n: the block of n; odd n: the next block
     bool odd = (n & 1);
-    load(blk);
+    load(seed, chain, blk);
     u = odd ? first_odd : c0;
     v = odd ? c0 : c1;
     n += 2;
@@ -185,11 +183,11 @@ struct RandomStream {
 };
 
 // rnorm -- mcmc.js:43-54 (Leva ratio-of-uniforms; two uniforms per trial)
-__device__ __forceinline__ double js_rnorm(RandomStream& g, double mean, double sd) {
+__device__ __forceinline__ double js_rnorm(RandomStream& g, uint64_t seed, uint64_t chain, double mean, double sd) {
   double u, v, x, y, q;
   do {
     double r;
-    g.next2(u, r);
+    g.next2(seed, chain, u, r);
     v = 1.7156 * (r - 0.5);
     x = u - 0.449871;
     y = fabs(v) + 0.386595;

@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
     unsigned long long ch = tid + (unsigned long long)k * T;
     valid[k] = ch < C;
     chain[k] = valid[k] ? ch : C - 1;                                // a missing chain shadows the last one and writes nothing
-    g[k].init(a.seed, a.first_chain + chain[k], a.rng_n[chain[k]]);
+    g[k].init(a.rng_n[chain[k]]);
     perm[k] = a.perm[chain[k]];
     curr[k] = a.curr_lp[chain[k]];
     es.st[k] = a.state + chain[k];
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
     for (int i = P - 1; i > 0; --i) {
 #pragma unroll
       for (int k = 0; k < W; ++k) {
-        int j = (int)floor(g[k].next() * (i + 1));
+        int j = (int)floor(g[k].next(a.seed, a.first_chain + chain[k]) * (i + 1));
         unsigned long long vi = (perm[k] >> (4 * i)) & 15ull, vj = (perm[k] >> (4 * j)) & 15ull;
         perm[k] = (perm[k] & ~(15ull << (4 * i))) | (vj << (4 * i));
         perm[k] = (perm[k] & ~(15ull << (4 * j))) | (vi << (4 * j));
@@ -358,7 +358,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
           // nested_array_random_apply: fresh identity, shuffled, top level only (mcmc.js:246-252)
           for (int i = 0; i < pa.dim0; ++i) order[k][i] = (unsigned char)i;
           for (int i = pa.dim0 - 1; i > 0; --i) {
-            int j = (int)floor(g[k].next() * (i + 1));
+            int j = (int)floor(g[k].next(a.seed, a.first_chain + chain[k]) * (i + 1));
             unsigned char t = order[k][i]; order[k][i] = order[k][j]; order[k][j] = t;
           }
         }
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
               prop[k] = (cur[k] == 0.0) ? 1.0 : 0.0;
               need[k] = true;
             } else {
-              prop[k] = js_rnorm(g[k], cur[k], a.psd[(unsigned long long)c[k] * C + chain[k]]);
+              prop[k] = js_rnorm(g[k], a.seed, a.first_chain + chain[k], cur[k], a.psd[(unsigned long long)c[k] * C + chain[k]]);
               if (pa.type == AMWG_INT) prop[k] = js_round(prop[k]);
               need[k] = !(prop[k] < pa.lower || prop[k] > pa.upper);
             }
@@ -422,13 +422,13 @@ __global__ void __launch_bounds__(kThreads, AMWG_WIDE_MINBLOCKS) amwg_sweep_kern
             double mx = js_max(z0raw, z1raw);
             double z0 = z0raw - mx, z1 = z1raw - mx;
             double zero_prob = js_exp(z0 - js_log(js_exp(z0) + js_exp(z1)));
-            bool zero = g[k].next() < zero_prob;
+            bool zero = g[k].next(a.seed, a.first_chain + chain[k]) < zero_prob;
             if (valid[k]) a.state[ci] = zero ? 0.0 : 1.0;
             curr[k] = zero ? z0raw : z1raw;
           } else if (need[k]) {
             // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
             double accept_prob = js_exp(lp_new[k] - curr[k]);
-            if (accept_prob > g[k].next()) {
+            if (accept_prob > g[k].next(a.seed, a.first_chain + chain[k])) {
               curr[k] = lp_new[k];
               if (valid[k]) {
                 a.state[ci] = prop[k];
