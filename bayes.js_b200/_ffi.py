@@ -60,7 +60,7 @@ class AmwgModel(C.Structure):
                 ("variant_logpost", C.POINTER(C.c_int32)), ("variant_derived", C.POINTER(C.c_int32))]
 
 
-EXPORTS = ["amwg_create", "amwg_destroy", "amwg_burn", "amwg_sample", "amwg_sample_device", "amwg_get_state",
+EXPORTS = ["amwg_create", "amwg_destroy", "amwg_burn", "amwg_sample", "amwg_sample_device", "amwg_get_state", "amwg_get_log_post",
            "amwg_set_adapting", "amwg_info", "amwg_kernel_launches", "amwg_last_sweep_kernel_ms", "amwg_n_chains",
            "amwg_last_error", "amwg_abi_version", "amwg_ld_eval", "amwg_primitive_eval"]
 
@@ -89,6 +89,7 @@ def lib():
     L.amwg_sample.argtypes = [vp, i64, i64, pi, i32, vp]; L.amwg_sample.restype = C.c_int
     L.amwg_sample_device.argtypes = [vp, i64, i64, pi, i32, vp]; L.amwg_sample_device.restype = C.c_int
     L.amwg_get_state.argtypes = [vp, vp]; L.amwg_get_state.restype = C.c_int
+    L.amwg_get_log_post.argtypes = [vp, vp]; L.amwg_get_log_post.restype = C.c_int
     L.amwg_set_adapting.argtypes = [vp, i32]; L.amwg_set_adapting.restype = C.c_int
     L.amwg_info.argtypes = [vp, vp, vp, vp]; L.amwg_info.restype = C.c_int
     L.amwg_kernel_launches.argtypes = [vp]; L.amwg_kernel_launches.restype = i64

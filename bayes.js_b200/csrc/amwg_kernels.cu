@@ -1295,6 +1295,14 @@ extern "C" int amwg_get_state(amwg_sampler* s, double* host_out) {
   return 0;
 }
 
+extern "C" int amwg_get_log_post(amwg_sampler* s, double* host_out) {
+  if (!s || !host_out) return fail("amwg_get_log_post: NULL argument");
+  CUDA_TRY(cudaSetDevice(s->device));
+  CUDA_TRY(cudaMemcpyAsync(host_out, s->a.curr_lp, sizeof(double) * (size_t)s->a.C, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
 extern "C" int amwg_set_adapting(amwg_sampler* s, int32_t flag) {
   if (!s) return fail("amwg_set_adapting: NULL handle");
   CUDA_TRY(cudaSetDevice(s->device));

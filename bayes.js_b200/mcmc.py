@@ -467,6 +467,12 @@ class AmwgSampler(Sampler):
             out[name] = self._shape_out(name, buf[e][None, :, :])[0]
         return out
 
+    def log_post(self):
+        """mcmc.js:958-960 -- `sampler.log_post()`: log_post at the current state (one number, or one per chain)."""
+        buf = np.empty(self.local_chains)
+        _ffi.check(_ffi.lib().amwg_get_log_post(self._handle, buf.ctypes.data))
+        return float(buf[0]) if self.n_chains == 1 else buf
+
     def burn(self, n_iterations):
         """mcmc.js:1035-1039"""
         L = _ffi.lib()

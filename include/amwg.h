@@ -203,6 +203,9 @@ AMWG_API int amwg_sample_device(amwg_sampler* s, int64_t n, int64_t thin, const 
 /* live state, as sampler.step() returns it (mcmc.js:985-997): out[entry][chain], entries = n_comp + n_derived */
 AMWG_API int amwg_get_state(amwg_sampler* s, double* host_out);
 
+/* sampler.log_post() -- the closure the Sampler ctor stores (mcmc.js:958-960): log_post at the chain's current state, out[chain] */
+AMWG_API int amwg_get_log_post(amwg_sampler* s, double* host_out);
+
 /* sampler.start_adaptation() / stop_adaptation() -- mcmc.js:1060-1073 */
 AMWG_API int amwg_set_adapting(amwg_sampler* s, int32_t flag);
 

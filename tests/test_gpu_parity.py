@@ -187,3 +187,61 @@ def test_chain_sharding_invariance(gpu_pkg):
     b = half.sample(60)
     assert np.array_equal(a["theta"][:, 64:], b["theta"])
     assert np.array_equal(a["m"][:, 64:], b["m"])
+
+
+def test_log_post_method_and_the_rest_of_the_ld_surface(gpu_pkg, orc):
+    """`sampler.log_post()` (the closure the Sampler ctor stores, mcmc.js:958-960) and every remaining `ld.*` function, including the
+    array-valued ones (bivarnorm, dirichlet, cat), evaluated through a traced log_post against the oracle's restatement."""
+    import ctypes
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    O = orc.lib()
+    # README model at its deterministic init (mu = sigma = 0.5): SURVEY 8(c) known answer
+    s = mcmc.AmwgSampler(models.PARAMS_NORM, models.norm_post_readme(ld), PRESIDENTS, {"seed": 1, "faithful": True})
+    ref = orc.OracleSampler("norm_readme", PRESIDENTS, models.PARAMS_NORM)
+    fn = O.orc_model_norm_readme
+    fn.restype = ctypes.c_double
+    fn.argtypes = [ctypes.c_void_p] * 3
+    st = ref.state()
+    want = fn(st.ctypes.data, ctypes.cast(ctypes.pointer(ref._keep[-1]), ctypes.c_void_p), None)
+    assert s.log_post() == want and abs(want - (-677441.3872049316)) < 1e-6
+    fast = mcmc.AmwgSampler(models.PARAMS_NORM, models.norm_post_readme(ld), PRESIDENTS, {"seed": 1})
+    assert abs(fast.log_post() - want) <= 1e-12 * abs(want)
+    fast.burn(25)
+    lp = fast.log_post()
+    stt = fast.state
+    arr = np.array([stt["mu"], stt["sigma"]])
+    assert abs(lp - fn(arr.ctypes.data, ctypes.cast(ctypes.pointer(ref._keep[-1]), ctypes.c_void_p), None)) <= 1e-12 * abs(lp)
+
+    def everything(state, data):
+        x = state.x
+        lp = 0
+        lp += ld.bivarnorm([x, 1.5], [0.5, 1.0], [1.2, 0.7], 0.3)
+        lp += ld.dirichlet([0.2, 0.3, 0.5], [1.5, x + 1, 3.0])
+        lp += ld.cat(2, [0.2, 0.5, 0.3])
+        lp += ld.t(x, 0.3, 1.2, 5)
+        lp += ld.weibull(x + 1, 1.5, 2.0)
+        lp += ld.gamma(x + 1, 2.0, 3.0) + ld.invgamma(x + 1, 2.0, 3.0) + ld.lnorm(x + 1, 0.2, 0.7) + ld.pareto(x + 3, 2.0, 3.0)
+        lp += ld.logis(x, 0.1, 0.9) + ld.exp(x, 1.3) + ld.binom(3, 10, x / 2) + ld.nbinom(4, 3, x / 2) + ld.hyper(2, 12, 9, 6)
+        lp += ld.cauchy(x, 0.2, 1.1) + ld.laplace(x, 0.2, 1.1) + ld.dexp(x, 0.2, 1.1)
+        lp += ld.lgamma(x + 2) + ld.lfactorial(4) + ld.lchoose(7, 3) + ld.lbeta(x + 1, 2.5)
+        return lp
+    s = mcmc.AmwgSampler({"x": {"type": "real", "lower": 0, "upper": 1}}, everything, None, {"seed": 3})
+    x = 0.5
+    a = lambda v: np.array(v, dtype=np.float64)          # noqa: E731
+    xv, mv, sv = a([x, 1.5]), a([0.5, 1.0]), a([1.2, 0.7])
+    dx, da = a([0.2, 0.3, 0.5]), a([1.5, x + 1, 3.0])
+    pr = a([0.2, 0.5, 0.3])
+    want = 0.0
+    want += O.orc_ld_bivarnorm(xv.ctypes.data, mv.ctypes.data, sv.ctypes.data, 0.3)
+    want += O.orc_ld_dirichlet(dx.ctypes.data, da.ctypes.data, 3)
+    want += O.orc_ld_cat(2.0, pr.ctypes.data, 3)
+    want += O.orc_ld_t(x, 0.3, 1.2, 5)
+    want += O.orc_ld_weibull(x + 1, 1.5, 2.0)
+    want += O.orc_ld_gamma(x + 1, 2.0, 3.0) + O.orc_ld_invgamma(x + 1, 2.0, 3.0) + O.orc_ld_lnorm(x + 1, 0.2, 0.7) + O.orc_ld_pareto(x + 3, 2.0, 3.0)
+    want += O.orc_ld_logis(x, 0.1, 0.9) + O.orc_ld_exp(x, 1.3) + O.orc_ld_binom(3, 10, x / 2) + O.orc_ld_nbinom(4, 3, x / 2) + O.orc_ld_hyper(2, 12, 9, 6)
+    want += O.orc_ld_cauchy(x, 0.2, 1.1) + O.orc_ld_laplace(x, 0.2, 1.1) + O.orc_ld_laplace(x, 0.2, 1.1)
+    want += O.orc_ld_lgamma(x + 2) + O.orc_ld_lfactorial(4) + O.orc_ld_lchoose(7, 3) + O.orc_ld_lbeta(x + 1, 2.5)
+    got = s.log_post()
+    assert abs(got - want) <= 1e-13 * abs(want), (got, want)
+    s.burn(50)
+    assert np.isfinite(s.log_post()) and 0 <= s.state["x"] <= 1
