@@ -21,7 +21,7 @@ OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)
 REAL, INT, BINARY = 0, 1, 2
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 
 class AmwgParam(C.Structure):
@@ -56,6 +56,7 @@ class AmwgModel(C.Structure):
                 ("n_fold", C.c_int32), ("fold_prog", C.POINTER(C.c_int32)), ("fold_dst", C.POINTER(C.c_int32)),
                 ("n_terms", C.c_int32), ("comp_prog", C.POINTER(C.c_int32)),
                 ("touch_off", C.POINTER(C.c_int32)), ("touch_terms", C.POINTER(C.c_int32)),
+                ("n_block_params", C.c_int32), ("block_params", C.POINTER(C.c_int32)), ("term_block_comp", C.POINTER(C.c_int32)),
                 ("n_variant_comps", C.c_int32), ("variant_comps", C.POINTER(C.c_int32)),
                 ("variant_logpost", C.POINTER(C.c_int32)), ("variant_derived", C.POINTER(C.c_int32))]
 

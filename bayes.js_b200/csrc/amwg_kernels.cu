@@ -57,6 +57,9 @@ struct ModelDev {
   unsigned off_code, off_consts, off_plates, off_params;
   unsigned off_comp_prog, off_touch_off, off_touch_terms;   // dependency-aware evaluation tables (amwg_model.comp_prog ...), valid when n_terms > 0
   int n_terms;                     // > 0: per-chain term cache in use
+  int n_block_params;              // multi-dim parameters stepped with one evaluation (amwg_model.block_params)
+  int block_params[AMWG_MAX_BLOCK_PARAMS];
+  unsigned off_tbc;                // image offset of term_block_comp [n_block_params][n_terms]
   const double* col_global[kMaxColumns];
   unsigned col_bytes[kMaxColumns];     // padded to 16
   int col_smem_off[kMaxColumns];       // byte offset in dynamic smem, or -1: read from global/L2
@@ -79,6 +82,8 @@ struct ChainArrays {
   double* curr_lp;        // [C]   cached log_post(state)
   double* tval;           // [n_terms][C] term cache: value of every value-term of log_post at the chain's current state
   double* tcand;          // [n_terms][C] candidates written while a proposal is evaluated; committed on acceptance
+  double* bprop;          // [D][C] block steps: the proposal of every component of the block (its current value when out of bounds)
+  double* bcoin;          // [D][C] block steps: the accept uniform drawn for it (-1: proposal out of bounds, no uniform drawn)
   unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
   unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
   unsigned long long C;
@@ -104,6 +109,7 @@ struct Ctx {                       // lives in shared memory
   const int* comp_prog;            // per-component programs / touched-term lists (n_terms > 0)
   const int* touch_off;
   const int* touch_terms;
+  const int* tbc;                  // term_block_comp
   const double* col[kMaxColumns];  // generic pointers (shared or global)
   unsigned col_saddr[kMaxColumns]; // 32-bit shared-window address, 0 when the column is served from global/L2
   double norm_c0;                  // -0.5 * Math.log(2 * Math.PI), evaluated once per CTA with the device's js_log
@@ -136,6 +142,12 @@ struct EvalStateT<true> : EvalStateBase {
   double* tcand = nullptr;
   unsigned long long tstride = 0;
   bool direct = false;        // STORE writes the cache itself (initial full evaluation) instead of the candidate slots
+  const double* bprop = nullptr;   // block step: components [blk_lo, blk_hi) are read from the chain's proposal array
+  int blk_lo = 0, blk_hi = 0;
+  __device__ __forceinline__ double comp(int c) const {
+    if (c >= blk_lo && c < blk_hi) return bprop[(unsigned long long)c * tstride];
+    return c == moved ? val : st[(unsigned long long)c * stride];
+  }
   __device__ __forceinline__ void store(int t, double v) const { if (tval) (direct ? tval : tcand)[(unsigned long long)t * tstride] = v; }
   __device__ __forceinline__ double cached(int t) const { return tval[(unsigned long long)t * tstride]; }
 };
@@ -192,6 +204,7 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
     ctx.comp_prog = reinterpret_cast<const int*>(smem + m.off_comp_prog);
     ctx.touch_off = reinterpret_cast<const int*>(smem + m.off_touch_off);
     ctx.touch_terms = reinterpret_cast<const int*>(smem + m.off_touch_terms);
+    ctx.tbc = reinterpret_cast<const int*>(smem + m.off_tbc);
     for (int k = 0; k < m.n_columns; ++k) {
       bool in_smem = m.col_smem_off[k] >= 0;
       ctx.col[k] = in_smem ? reinterpret_cast<const double*>(smem + m.col_smem_off[k]) : m.col_global[k];
@@ -730,6 +743,64 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
         }
       }
+      int block_slot = -1;
+      if constexpr (CACHE) {
+        const int pidx = (int)((perm >> (4 * slot)) & 15ull);
+        for (int k = 0; k < m.n_block_params; ++k) if (m.block_params[k] == pidx) block_slot = k;
+      }
+      if (CACHE && block_slot >= 0) {
+        // ======== block step: all components of this parameter with ONE evaluation (amwg.h block_params) ========
+        // 1. proposals and accept uniforms in the chain's visiting order: the Math.random() calls of mcmc.js:519-528, in order
+        if (sync) __syncthreads();
+        for (int r = 0; r < n_rounds; ++r) {
+          const int c = pa.comp_offset + (int)order[r / inner] * inner + (r % inner);
+          const unsigned long long ci = (unsigned long long)c * C + chain;
+          const double cur = a.state[ci];
+          double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci]);
+          if (pa.type == AMWG_INT) prop = js_round(prop);
+          const bool inb = !(prop < pa.lower || prop > pa.upper);
+          const double coin = inb ? g.next(a.seed, gchain) : -1.0;
+          if (valid) { a.bprop[ci] = inb ? prop : cur; a.bcoin[ci] = coin; }
+        }
+        // 2. the full program once, with every component of the block at its proposal: each term's candidate value -> tcand
+        if (sync) __syncthreads(); else __syncwarp(__activemask());
+        {
+          EvalStateT<CACHE> es{st, C, -1, 0.0};
+          if constexpr (CACHE) {
+            es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
+            es.bprop = a.bprop + chain; es.blk_lo = pa.comp_offset; es.blk_hi = pa.comp_offset + pa.n_comp;
+          }
+          (void)eval_logpost<CACHE>(ctx, es, m.logpost_prog);
+        }
+        if (sync) __syncthreads();
+        // 3. accept / reject one component at a time, in visiting order: log_post of "component c at its proposal" is the in-order
+        //    sum of the cached terms with c's terms taken from the candidates -- what the per-component program would have added
+        const int* tbc = ctx.tbc + block_slot * m.n_terms;
+        for (int r = 0; r < n_rounds; ++r) {
+          const int c = pa.comp_offset + (int)order[r / inner] * inner + (r % inner);
+          const unsigned long long ci = (unsigned long long)c * C + chain;
+          const double coin = a.bcoin[ci];
+          if (coin < 0.0) continue;                          // out of bounds: rejected without evaluation (mcmc.js:520-522)
+          double lp_new = 0.0;
+          for (int t = 0; t < m.n_terms; ++t) {
+            const unsigned long long ti = (unsigned long long)t * C + chain;
+            lp_new = lp_new + (tbc[t] == c ? a.tcand[ti] : a.tval[ti]);
+          }
+          const double accept_prob = js_exp(lp_new - curr);
+          if (accept_prob > coin) {
+            curr = lp_new;
+            if (valid) {
+              st[(unsigned long long)c * C] = a.bprop[ci];
+              if (m.adapting[c]) a.acc[ci] += 1;
+              for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
+                const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
+                a.tval[ti] = a.tcand[ti];
+              }
+            }
+          }
+        }
+        continue;
+      }
       for (int r = 0; r < n_rounds; ++r) {
         // ---- phase 1: propose
         if (sync) __syncthreads();
@@ -756,7 +827,8 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           int pc;
           if constexpr (CACHE) {                          // dependency-aware: only the terms that read component c are recomputed
             es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
-            pc = ctx.comp_prog[c];
+            // with the tile ring every lane must walk the same plates in the same order: everybody runs the full program
+            pc = ctx.ring_saddr ? m.logpost_prog : ctx.comp_prog[c];
           } else {
             pc = logpost_pc(m, es);
           }
@@ -966,6 +1038,9 @@ static int validate_model(const amwg_model* md) {
   for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v)
     if (md->variant_logpost[v] < 0 || md->variant_logpost[v] >= md->n_code) return fail("amwg_create: variant program out of range");
   if (md->n_derived > 0 && (md->derived_prog < 0 || md->derived_prog >= md->n_code)) return fail("amwg_create: derived_prog out of range");
+  if (md->n_block_params < 0 || md->n_block_params > AMWG_MAX_BLOCK_PARAMS) return fail("amwg_create: at most 4 block-stepped parameters are supported");
+  for (int k = 0; k < md->n_block_params; ++k)
+    if (md->block_params[k] < 0 || md->block_params[k] >= md->n_params) return fail("amwg_create: block_params out of range");
   if (md->comp_prog && md->n_terms > 0) {
     if (!md->touch_off || !md->touch_terms) return fail("amwg_create: comp_prog without touch lists");
     if (md->n_variant_comps > 0) return fail("amwg_create: comp_prog cannot be combined with variant programs");
@@ -1043,6 +1118,10 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   m.off_comp_prog = append(md->comp_prog, m.n_terms ? sizeof(int32_t) * (size_t)md->n_comp : 0);
   m.off_touch_off = append(md->touch_off, m.n_terms ? sizeof(int32_t) * (size_t)(md->n_comp + 1) : 0);
   m.off_touch_terms = append(md->touch_terms, m.n_terms ? sizeof(int32_t) * (size_t)md->touch_off[md->n_comp] : 0);
+  m.n_block_params = (m.n_terms && md->block_params && md->term_block_comp) ? md->n_block_params : 0;
+  if (const char* e = getenv("AMWG_BLOCK_STEPS")) { if (atoi(e) == 0) m.n_block_params = 0; }
+  for (int k = 0; k < m.n_block_params; ++k) m.block_params[k] = md->block_params[k];
+  m.off_tbc = append(md->term_block_comp, m.n_block_params ? sizeof(int32_t) * (size_t)m.n_block_params * (size_t)m.n_terms : 0);
   m.image_bytes = (unsigned)image.size();
   unsigned char* d_image = nullptr;
   if (dev_upload(s, image.data(), image.size(), &d_image)) return bail(-1);
@@ -1056,8 +1135,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     m.variant_derived[v] = md->variant_derived ? md->variant_derived[v] : -1;
   }
   {
-    bool all_scalar = true;
-    for (int p = 0; p < md->n_params; ++p) all_scalar = all_scalar && md->params[p].n_comp == 1;
+    bool all_scalar = true;                       // "scalar" = one evaluation per sweep slot: scalar parameters and block-stepped ones
+    for (int p = 0; p < md->n_params; ++p) {
+      bool block = false;
+      for (int k = 0; k < m.n_block_params; ++k) block = block || m.block_params[k] == p;
+      all_scalar = all_scalar && (md->params[p].n_comp == 1 || block);
+    }
     m.phase_sync = (all_scalar || md->n_params == 1) ? 1 : 0;
     if (const char* e = getenv("AMWG_PHASE_SYNC")) m.phase_sync = m.phase_sync && atoi(e) != 0;
   }
@@ -1102,7 +1185,8 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   if (dev_alloc(s, DC, &a.state) || dev_alloc(s, DC, &a.pls) || dev_alloc(s, DC, &a.psd) || dev_alloc(s, DC, &a.acc) || dev_alloc(s, (size_t)n_chains, &a.curr_lp) ||
       dev_alloc(s, (size_t)n_chains, &a.perm) || dev_alloc(s, (size_t)n_chains, &a.rng_n))
     return bail(-1);
-  a.tval = a.tcand = nullptr;
+  a.tval = a.tcand = a.bprop = a.bcoin = nullptr;
+  if (m.n_block_params > 0 && (dev_alloc(s, DC, &a.bprop) || dev_alloc(s, DC, &a.bcoin))) return bail(-1);
   if (m.n_terms > 0) {
     if (dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tval) || dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tcand)) return bail(-1);
     s->chains_per_thread = 1;            // the experimental wide kernel evaluates the full program only

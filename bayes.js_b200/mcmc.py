@@ -401,7 +401,12 @@ class AmwgSampler(Sampler):
         m.comp_prog = comp_prog.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
         m.touch_off = touch_off.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
         m.touch_terms = touch_terms.ctypes.data_as(C.POINTER(C.c_int32)) if prog.n_terms else None
-        self._cache_keepalive = (comp_prog, touch_off, touch_terms)
+        block_params = np.asarray(prog.block_params if prog.block_params else [0], dtype=np.int32)
+        tbc = np.asarray(prog.term_block_comp if prog.term_block_comp else [0], dtype=np.int32)
+        m.n_block_params = len(prog.block_params)
+        m.block_params = block_params.ctypes.data_as(C.POINTER(C.c_int32)) if prog.block_params else None
+        m.term_block_comp = tbc.ctypes.data_as(C.POINTER(C.c_int32)) if prog.block_params else None
+        self._cache_keepalive = (comp_prog, touch_off, touch_terms, block_params, tbc)
         vcomps = np.asarray(prog.variant_comps if prog.variant_comps else [0], dtype=np.int32)
         vlp = np.asarray(prog.variant_logpost if prog.variant_logpost else [0], dtype=np.int32)
         vder = np.asarray(prog.variant_derived if prog.variant_derived else [-1], dtype=np.int32)

@@ -316,6 +316,8 @@ class Program:
         self.comp_prog: List[int] = []
         self.touch_off: List[int] = []
         self.touch_terms: List[int] = []
+        self.block_params: List[int] = []      # parameters stepped with one evaluation (amwg.h block_params) ...
+        self.term_block_comp: List[int] = []   # ... and, per such parameter, the component of it each term reads (-1: none)
         self.variant_comps: List[int] = []     # binary components whose configuration selects the program (amwg.h variant_*)
         self.variant_logpost: List[int] = []
         self.variant_derived: List[int] = []
@@ -555,9 +557,10 @@ def _index_free(node: Sym) -> bool:
 
 
 class Lowering:
-    def __init__(self, tracer: Tracer, n_comp: int, faithful: bool = False):
+    def __init__(self, tracer: Tracer, n_comp: int, faithful: bool = False, param_ranges: Optional[List[Tuple[int, int, str]]] = None):
         self.t = tracer
         self.n_comp = n_comp
+        self.param_ranges = param_ranges or []   # (first component, number of components, type) per named parameter, in order
         self.faithful = faithful                 # True: no factorised plates -- every likelihood loop is added term by term like the JS loop
         self.prog = Program()
         self.prog.columns = tracer.columns       # shared list: synthesized columns are appended
@@ -860,6 +863,23 @@ class Lowering:
             p.emit("END")
         p.touch_off.append(len(p.touch_terms))
         p.summary.append(f"dependency-aware evaluation: {len(terms)} terms, cost {sum(per_comp) / (full * self.n_comp):.2f} of the full program")
+        # block steps: multi-dim parameters whose components never share a term (amwg.h block_params)
+        if all(tr["kind"] == "value" for tr in terms):
+            for pidx, (off, n, ptype) in enumerate(self.param_ranges):
+                if n <= 1 or ptype == "binary" or len(p.block_params) >= 4:
+                    continue
+                comps = set(range(off, off + n))
+                row = []
+                for tr in terms:
+                    hit = tr["deps"] & comps
+                    if len(hit) > 1:
+                        row = None
+                        break
+                    row.append(next(iter(hit)) if hit else -1)
+                if row is not None:
+                    p.block_params.append(pidx)
+                    p.term_block_comp.extend(row)
+                    p.summary.append(f"block steps for parameter #{pidx}: {n} components with one evaluation")
 
     def _per_component_cost(self) -> List[int]:
         terms = self._terms
@@ -1026,7 +1046,8 @@ def trace(log_post, params: Dict[str, dict], offsets: Dict[str, int], n_comp: in
     evaluated state, amwg.h variant_*): `if (m === 0) ... else ...` of tests/test_data.js:163-168 can be written as is."""
     tr = Tracer()
     wrapped = tr.wrap_data(data)
-    low = Lowering(tr, n_comp, faithful)
+    ranges = [(offsets[name], int(np.prod(p["dim"])), p["type"]) for name, p in params.items()]
+    low = Lowering(tr, n_comp, faithful, ranges)
     try:
         result, derived = _run_closure(tr, log_post, params, offsets, wrapped)
     except NeedsConcrete as exc:

@@ -28,7 +28,8 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 6
+#define AMWG_ABI_VERSION 7
+#define AMWG_MAX_BLOCK_PARAMS 4
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
 #else
@@ -175,6 +176,14 @@ typedef struct {
    * touch_terms[touch_off[c] .. touch_off[c+1]) are committed. logpost_prog is the full program (it stores every value-term). */
   int32_t n_terms;          const int32_t* comp_prog;      /* n_comp word offsets, or NULL */
   const int32_t* touch_off; const int32_t* touch_terms;    /* n_comp + 1 offsets into touch_terms */
+  /* Block steps (optional, needs comp_prog). A multi-dim parameter whose components never share a term (every term reads at most
+   * one of them: the group means of a hierarchical model) can be stepped with ONE evaluation of the full program: the proposals
+   * (and accept uniforms) of all its components are drawn first, in the chain's random visiting order, the program is evaluated
+   * with all of them in place (every term's candidate value lands in the term cache), and the accept decisions are then taken one
+   * component at a time in visiting order from the cached terms -- the same sums, values and uniforms as stepping them one by
+   * one. block_params lists such parameters (indices into params[]); term_block_comp[k * n_terms + t] is the component of
+   * block_params[k] that term t reads, or -1. */
+  int32_t n_block_params;   const int32_t* block_params;   const int32_t* term_block_comp;
   int32_t n_variant_comps;  const int32_t* variant_comps;
   const int32_t* variant_logpost;  const int32_t* variant_derived;     /* 1 << n_variant_comps entries each (derived: -1 if none) */
 } amwg_model;

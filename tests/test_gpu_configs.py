@@ -103,16 +103,46 @@ def test_dependency_aware_evaluation_is_bit_identical_to_the_full_program(gpu_pk
     data = {"y": y.tolist(), "g": g.tolist()}
     mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
     out = {}
-    for flag in ("1", "0"):
-        os.environ["AMWG_TERM_CACHE"] = flag
+    for name, env in (("block", {}), ("cache", {"AMWG_BLOCK_STEPS": "0"}), ("full", {"AMWG_TERM_CACHE": "0"}), ("block_l2", {"AMWG_PHASE_SYNC": "0"})):
+        os.environ.update(env)
         try:
             s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 512, "seed": 12})
+            if name == "block":
+                assert any(x.startswith("block steps") for x in s.program_summary())
             s.burn(120)
-            out[flag] = s.sample(60)
+            out[name] = s.sample(60)
+            out[name + "_info"] = s.info()["steppers"][0]
         finally:
-            del os.environ["AMWG_TERM_CACHE"]
-    assert np.array_equal(out["1"]["mu"], out["0"]["mu"]) and np.array_equal(out["1"]["sigma"], out["0"]["sigma"])
-    assert out["1"]["mu"].std() > 0
+            for k in env:
+                del os.environ[k]
+    # block steps (all J group means with one evaluation), per-component cached programs, and the plain full program: same draws
+    for other in ("cache", "full", "block_l2"):
+        assert np.array_equal(out["block"]["mu"], out[other]["mu"]) and np.array_equal(out["block"]["sigma"], out[other]["sigma"]), other
+        assert np.array_equal(out["block_info"]["mu"]["prop_log_scale"], out[other + "_info"]["mu"]["prop_log_scale"])
+    assert out["block"]["mu"].std() > 0
+
+
+def test_block_steps_stream_the_data_through_the_tile_ring(gpu_pkg):
+    """config-4 shape with data that does not fit in shared memory (8 groups x 4096 points = 256 KB + the group column): with
+    block steps every chain takes one evaluation per sweep slot, so the CTA walks the plates together and the column goes through
+    the TMA tile ring; one tile per group here, so the sums are the same as on the L2 path -- identical draws."""
+    import os
+    J, per = 8, 4096
+    y, g, params = _hier(J, per, 66)
+    data = {"y": y.tolist(), "g": g.tolist()}
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    out = {}
+    for name, env in (("ring", {}), ("l2", {"AMWG_PHASE_SYNC": "0"})):
+        os.environ.update(env)
+        try:
+            s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 256, "seed": 13})
+            s.burn(60)
+            out[name] = s.sample(20)
+        finally:
+            for k in env:
+                del os.environ[k]
+    assert np.array_equal(out["ring"]["mu"], out["l2"]["mu"]) and np.array_equal(out["ring"]["sigma"], out["l2"]["sigma"])
+    assert abs(out["ring"]["mu"][-1, :, 0].mean() - y[g == 0].mean()) < 0.5
 
 
 def poisreg_post(ld, mcmc, K):
