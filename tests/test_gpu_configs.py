@@ -83,7 +83,7 @@ def test_config4_hierarchical_normal(gpu_pkg, orc):
     # fast path (one factorised plate per group): same posterior
     s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 4096, "seed": 6})
     assert [x for x in s.program_summary() if x.startswith("plate")] == [f"plate NORM_IID n={per}"] * J
-    assert s.program_summary()[-1].startswith("dependency-aware evaluation")
+    assert any(x.startswith("dependency-aware evaluation") for x in s.program_summary())
     s.burn(1500)
     fast = s.sample(1)
     ref = orc.run_model("hier_norm", {"y": y, "g": g}, params, chains=1024, seed=6, burn=1500, sample=1)
