@@ -748,87 +748,62 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         const int pidx = (int)((perm >> (4 * slot)) & 15ull);
         for (int k = 0; k < m.n_block_params; ++k) if (m.block_params[k] == pidx) block_slot = k;
       }
-      if (CACHE && block_slot >= 0) {
-        // ======== block step: all components of this parameter with ONE evaluation (amwg.h block_params) ========
-        // 1. proposals and accept uniforms in the chain's visiting order: the Math.random() calls of mcmc.js:519-528, in order
-        if (sync) __syncthreads();
-        for (int r = 0; r < n_rounds; ++r) {
-          const int c = pa.comp_offset + (int)order[r / inner] * inner + (r % inner);
-          const unsigned long long ci = (unsigned long long)c * C + chain;
-          const double cur = a.state[ci];
-          double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci]);
-          if (pa.type == AMWG_INT) prop = js_round(prop);
-          const bool inb = !(prop < pa.lower || prop > pa.upper);
-          const double coin = inb ? g.next(a.seed, gchain) : -1.0;
-          if (valid) { a.bprop[ci] = inb ? prop : cur; a.bcoin[ci] = coin; }
-        }
-        // 2. the full program once, with every component of the block at its proposal: each term's candidate value -> tcand
-        if (sync) __syncthreads(); else __syncwarp(__activemask());
-        {
-          EvalStateT<CACHE> es{st, C, -1, 0.0};
-          if constexpr (CACHE) {
-            es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
-            es.bprop = a.bprop + chain; es.blk_lo = pa.comp_offset; es.blk_hi = pa.comp_offset + pa.n_comp;
-          }
-          (void)eval_logpost<CACHE>(ctx, es, m.logpost_prog);
-        }
-        if (sync) __syncthreads();
-        // 3. accept / reject one component at a time, in visiting order: log_post of "component c at its proposal" is the in-order
-        //    sum of the cached terms with c's terms taken from the candidates -- what the per-component program would have added
-        const int* tbc = ctx.tbc + block_slot * m.n_terms;
-        for (int r = 0; r < n_rounds; ++r) {
-          const int c = pa.comp_offset + (int)order[r / inner] * inner + (r % inner);
-          const unsigned long long ci = (unsigned long long)c * C + chain;
-          const double coin = a.bcoin[ci];
-          if (coin < 0.0) continue;                          // out of bounds: rejected without evaluation (mcmc.js:520-522)
-          double lp_new = 0.0;
-          for (int t = 0; t < m.n_terms; ++t) {
-            const unsigned long long ti = (unsigned long long)t * C + chain;
-            lp_new = lp_new + (tbc[t] == c ? a.tcand[ti] : a.tval[ti]);
-          }
-          const double accept_prob = js_exp(lp_new - curr);
-          if (accept_prob > coin) {
-            curr = lp_new;
-            if (valid) {
-              st[(unsigned long long)c * C] = a.bprop[ci];
-              if (m.adapting[c]) a.acc[ci] += 1;
-              for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
-                const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
-                a.tval[ti] = a.tcand[ti];
-              }
-            }
-          }
-        }
-        continue;
-      }
-      for (int r = 0; r < n_rounds; ++r) {
+      // A block-stepped parameter (amwg.h block_params) takes ONE round for all its components; otherwise one round per component.
+      // Propose / evaluate / accept share their barrier points and the evaluation call site between the two kinds of round, so
+      // that lanes of one warp that drew different parameters for this slot still execute the same barriers (bar.sync is aligned)
+      // and, with the tile ring, walk the plates of the full program together.
+      const bool is_block = CACHE && block_slot >= 0;
+      const int rounds = is_block ? 1 : n_rounds;
+      for (int r = 0; r < rounds; ++r) {
         // ---- phase 1: propose
         if (sync) __syncthreads();
         int c = pa.comp_offset;
-        if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        if (!is_block && pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
         const unsigned long long ci = (unsigned long long)c * C;
-        const double cur = st[ci];
-        double prop;
+        double cur = 0.0, prop = 0.0;
         bool need;
-        if (pa.type == AMWG_BINARY) {
-          prop = (cur == 0.0) ? 1.0 : 0.0;               // the state value whose log_post is not cached
+        if (is_block) {
+          // proposals and accept uniforms of every component, in the chain's visiting order: the Math.random() calls of
+          // mcmc.js:519-528 in their original order (a uniform is only drawn for an in-bounds proposal)
+          for (int q = 0; q < n_rounds; ++q) {
+            const int cq = pa.comp_offset + (int)order[q / inner] * inner + (q % inner);
+            const unsigned long long cqi = (unsigned long long)cq * C + chain;
+            const double curq = a.state[cqi];
+            double pq = js_rnorm(g, a.seed, gchain, curq, a.psd[cqi]);
+            if (pa.type == AMWG_INT) pq = js_round(pq);
+            const bool inb = !(pq < pa.lower || pq > pa.upper);
+            const double coin = inb ? g.next(a.seed, gchain) : -1.0;
+            if (valid) { a.bprop[cqi] = inb ? pq : curq; a.bcoin[cqi] = coin; }
+          }
           need = true;
         } else {
-          // generate_proposal (mcmc.js:519, 577-579 / 596-598) and the bounds check (:520)
-          prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci + chain]);
-          if (pa.type == AMWG_INT) prop = js_round(prop);
-          need = !(prop < pa.lower || prop > pa.upper);
+          cur = st[ci];
+          if (pa.type == AMWG_BINARY) {
+            prop = (cur == 0.0) ? 1.0 : 0.0;               // the state value whose log_post is not cached
+            need = true;
+          } else {
+            // generate_proposal (mcmc.js:519, 577-579 / 596-598) and the bounds check (:520)
+            prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci + chain]);
+            if (pa.type == AMWG_INT) prop = js_round(prop);
+            need = !(prop < pa.lower || prop > pa.upper);
+          }
         }
         // ---- phase 2: evaluate log_post at the proposal (the O(N) likelihood sum)
         if (sync) __syncthreads(); else __syncwarp(__activemask());
         double lp_new = 0.0;
         if (need || ctx.ring_saddr) {                     // with the tile ring the plate is a CTA-wide collective: nobody may skip it
-          EvalStateT<CACHE> es{st, C, c, need ? prop : cur};
+          EvalStateT<CACHE> es{st, C, is_block ? -1 : c, need ? prop : cur};
           int pc;
-          if constexpr (CACHE) {                          // dependency-aware: only the terms that read component c are recomputed
+          if constexpr (CACHE) {
             es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
-            // with the tile ring every lane must walk the same plates in the same order: everybody runs the full program
-            pc = ctx.ring_saddr ? m.logpost_prog : ctx.comp_prog[c];
+            if (is_block) {                               // the whole block at its proposals: every term's candidate value -> tcand
+              es.bprop = a.bprop + chain; es.blk_lo = pa.comp_offset; es.blk_hi = pa.comp_offset + pa.n_comp;
+              pc = m.logpost_prog;
+            } else {
+              // dependency-aware: only the terms that read component c are recomputed; with the tile ring every lane must walk
+              // the same plates in the same order, so everybody runs the full program
+              pc = ctx.ring_saddr ? m.logpost_prog : ctx.comp_prog[c];
+            }
           } else {
             pc = logpost_pc(m, es);
           }
@@ -836,7 +811,34 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         }
         // ---- phase 3: accept / reject
         if (sync) __syncthreads();
-        if (pa.type == AMWG_BINARY) {
+        if (is_block) {
+          // one component at a time, in visiting order: log_post of "component c at its proposal" is the in-order sum of the cached
+          // terms with c's terms taken from the candidates -- exactly what the per-component program adds
+          const int* tbc = ctx.tbc + block_slot * m.n_terms;
+          for (int q = 0; q < n_rounds; ++q) {
+            const int cq = pa.comp_offset + (int)order[q / inner] * inner + (q % inner);
+            const unsigned long long cqi = (unsigned long long)cq * C + chain;
+            const double coin = a.bcoin[cqi];
+            if (coin < 0.0) continue;                        // out of bounds: rejected without evaluation (mcmc.js:520-522)
+            double lpq = 0.0;
+            for (int t = 0; t < m.n_terms; ++t) {
+              const unsigned long long ti = (unsigned long long)t * C + chain;
+              lpq = lpq + (tbc[t] == cq ? a.tcand[ti] : a.tval[ti]);
+            }
+            const double accept_prob = js_exp(lpq - curr);
+            if (accept_prob > coin) {
+              curr = lpq;
+              if (valid) {
+                a.state[cqi] = a.bprop[cqi];
+                if (m.adapting[cq]) a.acc[cqi] += 1;
+                for (int k = ctx.touch_off[cq]; k < ctx.touch_off[cq + 1]; ++k) {
+                  const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
+                  a.tval[ti] = a.tcand[ti];
+                }
+              }
+            }
+          }
+        } else if (pa.type == AMWG_BINARY) {
           // BinaryStepper.step (mcmc.js:753-767); log_post of the current value is the cached one
           double z0raw = (cur == 0.0) ? curr : lp_new, z1raw = (cur == 0.0) ? lp_new : curr;
           double mx = js_max(z0raw, z1raw);
