@@ -21,7 +21,7 @@ OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)
 REAL, INT, BINARY = 0, 1, 2
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 
 class AmwgParam(C.Structure):
@@ -63,7 +63,8 @@ class AmwgModel(C.Structure):
 
 EXPORTS = ["amwg_create", "amwg_destroy", "amwg_burn", "amwg_sample", "amwg_sample_device", "amwg_get_state", "amwg_get_log_post",
            "amwg_set_adapting", "amwg_info", "amwg_kernel_launches", "amwg_last_sweep_kernel_ms", "amwg_n_chains",
-           "amwg_last_error", "amwg_abi_version", "amwg_ld_eval", "amwg_primitive_eval"]
+           "amwg_last_error", "amwg_abi_version", "amwg_ld_eval", "amwg_primitive_eval",
+           "amwg_summary_moments", "amwg_summary_digit_hist"]
 
 _lib = None
 
@@ -100,6 +101,8 @@ def lib():
     L.amwg_abi_version.argtypes = []; L.amwg_abi_version.restype = C.c_int
     L.amwg_ld_eval.argtypes = [i32, vp, i32, i64, vp, C.c_int]; L.amwg_ld_eval.restype = C.c_int
     L.amwg_primitive_eval.argtypes = [i32, vp, i64, u64, u64, vp, C.c_int]; L.amwg_primitive_eval.restype = C.c_int
+    L.amwg_summary_moments.argtypes = [C.c_int, vp, i64, i32, i64, vp]; L.amwg_summary_moments.restype = C.c_int
+    L.amwg_summary_digit_hist.argtypes = [C.c_int, vp, i64, i32, i64, i32, vp, i32, vp]; L.amwg_summary_digit_hist.restype = C.c_int
     if L.amwg_abi_version() != ABI_VERSION:
         raise AmwgError("libamwg_b200.so ABI version mismatch")
     _lib = L

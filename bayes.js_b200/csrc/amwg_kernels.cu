@@ -1450,3 +1450,5 @@ extern "C" int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uin
   if (e != cudaSuccess) return fail(std::string("amwg_primitive_eval: ") + cudaGetErrorString(e));
   return 0;
 }
+
+#include "amwg_summary.cuh"

@@ -1,0 +1,142 @@
+// Post-path reductions on device. The reference hands back raw draws only (mcmc.js:1029) and leaves the
+// summary (mean / sd / quantiles, README.md:44-52 plots them) to the caller; with 2^20..2^22 chains the raw block is GBs, so the
+// summary is formed where the draws are and only a few hundred bytes cross PCIe / NVLink.
+//
+// Input everywhere: a device-resident sample block in amwg_sample_device's layout, x[row][entry][chain] (chain fastest).
+//   K_m1  amwg_chain_moments_kernel : one thread per (chain, entry): mean and M2 of the chain over its rows, two sequential passes
+//                                     (coalesced over chains; HBM-bound: 2 reads of the block)
+//   K_m2  amwg_merge_moments_kernel : one CTA per entry: Welford/Chan merge of the chain means in a FIXED order (strided
+//                                     per-thread runs, then a shared-memory tree), so the result does not depend on scheduling
+//   K_q   amwg_digit_hist_kernel    : one pass of an exact MSD radix select over the order-preserving 64-bit key of the draws:
+//                                     counts of the next 8-bit digit among the values whose higher digits equal a given prefix
+//                                     (integer counts: exact, order independent, summed across GPUs by the caller)
+// Included at the end of amwg_kernels.cu (same translation unit: shares CUDA_TRY / fail()).
+#pragma once
+
+namespace summary {
+
+constexpr int kMaxPrefixes = 32;      // distinct prefixes per entry and pass (order statistics being selected at once)
+
+__device__ __forceinline__ unsigned long long ordered_key(double x) {
+  unsigned long long u = (unsigned long long)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);      // ascending keys == ascending doubles (-0 < +0, NaN on top)
+}
+
+__global__ void __launch_bounds__(256) amwg_chain_moments_kernel(const double* __restrict__ x, long long rows, int entries, long long C,
+                                                                 double* __restrict__ cmean, double* __restrict__ cm2) {
+  const int e = blockIdx.y;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+    const double* p = x + (size_t)e * C + c;
+    const size_t stride = (size_t)entries * C;
+    double s = 0.0;
+    for (long long r = 0; r < rows; ++r) s += p[r * stride];
+    const double m = s / (double)rows;
+    double m2 = 0.0;
+    for (long long r = 0; r < rows; ++r) { double d = p[r * stride] - m; m2 = fma(d, d, m2); }
+    cmean[(size_t)e * C + c] = m;
+    cm2[(size_t)e * C + c] = m2;
+  }
+}
+
+struct Moments { double n, mean, m2, sum_w; };     // n chain means merged so far; sum_w = sum of the within-chain M2
+
+__device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
+  if (b.n == 0.0) return a;
+  if (a.n == 0.0) return b;
+  Moments r;
+  r.n = a.n + b.n;
+  const double d = b.mean - a.mean;
+  r.mean = a.mean + d * (b.n / r.n);
+  r.m2 = a.m2 + b.m2 + d * d * (a.n * b.n / r.n);
+  r.sum_w = a.sum_w + b.sum_w;
+  return r;
+}
+
+// out[entry][4] = {chains, mean of the chain means, M2 of the chain means, sum over chains of the within-chain M2}
+__global__ void __launch_bounds__(1024) amwg_merge_moments_kernel(const double* __restrict__ cmean, const double* __restrict__ cm2, long long C,
+                                                                  double* __restrict__ out) {
+  __shared__ Moments sh[1024];
+  const int e = blockIdx.x, t = threadIdx.x;
+  Moments acc{0.0, 0.0, 0.0, 0.0};
+  for (long long c = t; c < C; c += blockDim.x) {           // fixed order per thread
+    Moments one{1.0, cmean[(size_t)e * C + c], 0.0, cm2[(size_t)e * C + c]};
+    acc = merge(acc, one);
+  }
+  sh[t] = acc;
+  __syncthreads();
+  for (int w = blockDim.x >> 1; w > 0; w >>= 1) {            // fixed tree
+    if (t < w) sh[t] = merge(sh[t], sh[t + w]);
+    __syncthreads();
+  }
+  if (t == 0) { out[e * 4 + 0] = sh[0].n; out[e * 4 + 1] = sh[0].mean; out[e * 4 + 2] = sh[0].m2; out[e * 4 + 3] = sh[0].sum_w; }
+}
+
+// counts[entry][prefix][256] += number of values of `entry` whose key's top 8*pass bits equal prefix[entry][p] and whose next
+// byte is the bin. Grid: (chain blocks, entries). Shared-memory histogram per CTA, flushed with 64-bit global atomics.
+__global__ void __launch_bounds__(256) amwg_digit_hist_kernel(const double* __restrict__ x, long long rows, int entries, long long C, int pass,
+                                                              const unsigned long long* __restrict__ prefix, int n_prefix,
+                                                              unsigned long long* __restrict__ counts) {
+  __shared__ unsigned int hist[kMaxPrefixes * 256];
+  __shared__ unsigned long long pre[kMaxPrefixes];
+  const int e = blockIdx.y;
+  for (int i = threadIdx.x; i < n_prefix * 256; i += blockDim.x) hist[i] = 0u;
+  if (threadIdx.x < n_prefix) pre[threadIdx.x] = prefix[(size_t)e * n_prefix + threadIdx.x];
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  const size_t stride = (size_t)entries * C;
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+    const double* p = x + (size_t)e * C + c;
+    for (long long r = 0; r < rows; ++r) {
+      const unsigned long long k = ordered_key(p[r * stride]);
+      const unsigned int bin = (unsigned int)(k >> shift) & 255u;
+      const unsigned long long hi = pass ? (k >> (shift + 8)) : 0ull;
+      for (int q = 0; q < n_prefix; ++q)
+        if (pass == 0 || hi == pre[q]) atomicAdd(&hist[q * 256 + bin], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n_prefix * 256; i += blockDim.x)
+    if (hist[i]) atomicAdd(&counts[(size_t)e * n_prefix * 256 + i], (unsigned long long)hist[i]);
+}
+
+}  // namespace summary
+
+extern "C" int amwg_summary_moments(int device, const double* dev_samples, int64_t rows, int32_t entries, int64_t chains, double* host_stats) {
+  if (rows <= 0 || entries <= 0 || chains <= 0) return fail("amwg_summary_moments: empty sample block");
+  if (!dev_samples || !host_stats) return fail("amwg_summary_moments: null pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  double *cmean = nullptr, *cm2 = nullptr, *d_out = nullptr;
+  const size_t n = (size_t)entries * (size_t)chains;
+  cudaError_t e = cudaMalloc(&cmean, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&cm2, n * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)entries * 4 * sizeof(double));
+  if (e == cudaSuccess) {
+    const unsigned bx = (unsigned)std::min<int64_t>((chains + 255) / 256, 148 * 8);
+    summary::amwg_chain_moments_kernel<<<dim3(bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, cmean, cm2);
+    summary::amwg_merge_moments_kernel<<<(unsigned)entries, 1024>>>(cmean, cm2, chains, d_out);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy(host_stats, d_out, (size_t)entries * 4 * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(cmean); cudaFree(cm2); cudaFree(d_out);
+  if (e != cudaSuccess) return fail(std::string("amwg_summary_moments: ") + cudaGetErrorString(e));
+  return 0;
+}
+
+extern "C" int amwg_summary_digit_hist(int device, const double* dev_samples, int64_t rows, int32_t entries, int64_t chains, int32_t pass,
+                                       const uint64_t* dev_prefix, int32_t n_prefix, uint64_t* dev_counts) {
+  if (rows <= 0 || entries <= 0 || chains <= 0) return fail("amwg_summary_digit_hist: empty sample block");
+  if (pass < 0 || pass > 7) return fail("amwg_summary_digit_hist: pass must be 0..7");
+  if (n_prefix < 1 || n_prefix > summary::kMaxPrefixes) return fail("amwg_summary_digit_hist: n_prefix must be 1.." + std::to_string(summary::kMaxPrefixes));
+  if (rows >= (int64_t)1 << 32) return fail("amwg_summary_digit_hist: more than 2^32 rows");
+  if (!dev_samples || !dev_prefix || !dev_counts) return fail("amwg_summary_digit_hist: null pointer");
+  CUDA_TRY(cudaSetDevice(device));
+  // a CTA's shared bins are 32-bit: bound the values one CTA sees by 2^32 (rows < 2^32 and the grid below keeps chains per CTA small)
+  int64_t bx = std::min<int64_t>((chains + 255) / 256, 148 * 8);
+  while (bx < (chains + 255) / 256 && ((chains + bx - 1) / bx) * rows >= ((int64_t)1 << 32)) bx *= 2;
+  summary::amwg_digit_hist_kernel<<<dim3((unsigned)bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, pass,
+                                                                                  reinterpret_cast<const unsigned long long*>(dev_prefix), n_prefix,
+                                                                                  reinterpret_cast<unsigned long long*>(dev_counts));
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaDeviceSynchronize());
+  return 0;
+}

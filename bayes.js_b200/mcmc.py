@@ -519,6 +519,52 @@ class AmwgSampler(Sampler):
             raise JsThrow(L.amwg_last_error().decode())
         return buf
 
+    def sample_summary(self, n_iterations, probs=(0.025, 0.25, 0.5, 0.75, 0.975)):
+        """Not in the reference: the same sweeps and the same kept rows as `sample(n)` (thin / monitor apply), but the
+        draws stay in HBM and only their summary comes back: {name: {"mean", "sd", "rhat", "quantiles", "n_draws"}}, pooled over
+        all chains and kept rows; multi-dim parameters give arrays of their `dim` ("quantiles": [len(probs), *dim], exact order
+        statistics with numpy.quantile's linear rule). With options.distributed every rank returns the all-GPU summary
+        (two small collectives, summary.py). Advances the chains exactly as sample(n) does."""
+        import torch
+        from .summary import CudaBlockReducer, summarise_block
+        monitored = self._state_keys() if self.monitored_params is None else list(self.monitored_params)
+        entries: List[int] = []
+        spans = {}
+        for name in monitored:
+            e = self._entries(name)
+            spans[name] = (len(entries), len(e))
+            entries.extend(e)
+        n = int(n_iterations)
+        thin = int(self.thinning_interval)
+        rows = 0 if n <= 0 else (n + thin - 1) // thin
+        if rows == 0 or not entries:
+            raise JsThrow("sample_summary needs at least one kept iteration and one monitored entry")
+        L = _ffi.lib()
+        dev = torch.device("cuda", self.device)
+        need = rows * len(entries) * self.local_chains * 8
+        free, _total = torch.cuda.mem_get_info(dev)
+        if need + 2 * len(entries) * self.local_chains * 8 > 0.9 * free:
+            raise JsThrow("sample_summary: the sample block (%.1f GB) does not fit in device memory; raise thin() or lower n" % (need / 1e9))
+        block = torch.empty((rows, len(entries), self.local_chains), dtype=torch.float64, device=dev)
+        mon = np.asarray(entries, dtype=np.int32)
+        torch.cuda.current_stream(dev).synchronize()
+        rc = L.amwg_sample_device(self._handle, n, thin, mon.ctypes.data_as(C.POINTER(C.c_int32)), len(entries), block.data_ptr())
+        if rc != 0:
+            raise JsThrow(L.amwg_last_error().decode())
+        mean, sd, rhat, q = summarise_block(CudaBlockReducer(self.device), block, rows, self.n_chains, probs, self.distributed)
+        del block
+        out = {}
+        for name in monitored:
+            s0, ln = spans[name]
+            if ln == 0:
+                continue
+            dim = list(self.params[name]["dim"]) if name in self.params else [1]
+            shape = (lambda a: float(a[0])) if dim == [1] else (lambda a, dim=dim: np.asarray(a).reshape(*dim))
+            out[name] = {"mean": shape(mean[s0:s0 + ln]), "sd": shape(sd[s0:s0 + ln]), "rhat": shape(rhat[s0:s0 + ln]),
+                         "quantiles": q[:, s0] if dim == [1] else q[:, s0:s0 + ln].reshape(len(q), *dim),
+                         "n_draws": rows * self.n_chains}
+        return out
+
     def start_adaptation(self):
         """mcmc.js:1060-1064"""
         _ffi.check(_ffi.lib().amwg_set_adapting(self._handle, 1))

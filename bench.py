@@ -210,10 +210,19 @@ def run_ours(args):
     dt_e2e = time.perf_counter() - t1
     assert draws["mu"].shape == (iters, chains_total if rank == 0 else local)      # gather="root": rank 0 holds every chain
 
-    times = torch.tensor([dt, dt_e2e, kernel_ms], dtype=torch.float64, device=f"cuda:{local_rank}")
+    # ---- e2e with the summary formed on the device: same sweeps, only mean/sd/quantiles/R-hat leave the GPUs
+    summ = sampler.sample_summary(iters)       # warm-up
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(e2e_steps):
+        summ = sampler.sample_summary(iters)
+    barrier()
+    dt_sum = time.perf_counter() - t2
+
+    times = torch.tensor([dt, dt_e2e, kernel_ms, dt_sum], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e, kernel_ms = [float(v) for v in times.tolist()]
+    dt, dt_e2e, kernel_ms, dt_sum = [float(v) for v in times.tolist()]
 
     if rank == 0:
         draws_per_step = chains_total * iters
@@ -246,6 +255,13 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(iters * 2 * chains_total * 8), "steps": e2e_steps,
                     "note": "mcmc.AmwgSampler.sample(): pinned host buffer, D2H overlapped with the sweeps"
                             + ("; NCCL gather of the shards to rank 0 first (gather=\"root\": one host copy of all draws)" if world > 1 else "")},
+            "e2e_summary": {"value": draws_per_step * e2e_steps / dt_sum, "unit": "draws/s", "steps": e2e_steps,
+                            "d2h_bytes_per_step": 2 * 4 * 8 + 8 * 2 * 10 * 256 * 8,
+                            "mu": {"mean": summ["mu"]["mean"], "sd": summ["mu"]["sd"], "rhat": summ["mu"]["rhat"],
+                                   "q2.5_50_97.5": [float(summ["mu"]["quantiles"][i]) for i in (0, 2, 4)]},
+                            "note": "mcmc.AmwgSampler.sample_summary(): the draws stay in HBM; pooled mean/sd, exact quantiles (8-pass radix "
+                                    "select) and R-hat over all chains x iterations come back"
+                                    + ("; shards combined by an all-gather of moment records and an all-reduce of digit counts (NCCL)" if world > 1 else "")},
             "gpu_launches": int(launches), "clocks": clk,
         }
         if world == 1 and not args.no_cpu:

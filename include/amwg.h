@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define AMWG_ABI_VERSION 7
+#define AMWG_ABI_VERSION 8
 #define AMWG_MAX_BLOCK_PARAMS 4
 #if defined(__GNUC__)
 #define AMWG_API __attribute__((visibility("default")))
@@ -238,6 +238,24 @@ AMWG_API int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t
 /* Math.log / Math.exp / the Philox uniform stream on the device, for parity tests of the primitives.
  * kind: 0 log, 1 exp, 2 stream uniform (x[i] reinterpreted: out[i] = uniform #i of chain `chain`), 3 rnorm(0,1) draw i.. */
 AMWG_API int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device);
+
+/* ---- post-path reductions on device ------------------------------------------------------------------
+ * The reference returns raw draws only (mcmc.js:1029; README.md:44-52 leaves the summary to the caller). With millions of
+ * chains the summary is formed where the draws are. Both calls read a DEVICE-resident sample block in amwg_sample_device's
+ * layout, x[row][entry][chain]; neither needs a sampler handle (they are reductions over the block).
+ *
+ * amwg_summary_moments: host_stats[entry][4] = { chains, mean of the per-chain means, M2 of the per-chain means
+ *   (sum_c (m_c - mean)^2), sum over chains of the within-chain M2 (sum_r (x_rc - m_c)^2) }, merged in a fixed order
+ *   (deterministic). Pooled mean / sd and the Gelman-Rubin statistic follow from these; shards (multi-GPU) merge exactly.
+ *
+ * amwg_summary_digit_hist: one pass (0..7, most significant byte first) of an exact radix select over the order-preserving
+ *   64-bit key of the draws: dev_counts[entry][prefix][256] += number of values of `entry` whose key's top 8*pass bits equal
+ *   dev_prefix[entry][prefix] and whose next byte is the bin (pass 0 ignores the prefixes). Integer counts: exact and
+ *   order-independent; the caller sums them over GPUs, picks the byte holding each wanted order statistic and extends the
+ *   prefixes. n_prefix <= 32. */
+AMWG_API int amwg_summary_moments(int device, const double* dev_samples, int64_t rows, int32_t entries, int64_t chains, double* host_stats);
+AMWG_API int amwg_summary_digit_hist(int device, const double* dev_samples, int64_t rows, int32_t entries, int64_t chains, int32_t pass,
+                                     const uint64_t* dev_prefix, int32_t n_prefix, uint64_t* dev_counts);
 
 #ifdef __cplusplus
 }

@@ -31,7 +31,7 @@ def orc():
 def gpu_pkg(pkg):
     """The package with the CUDA library loaded; GPU tests fail loudly if the extension is missing."""
     lib = pkg._ffi.lib()
-    assert lib.amwg_abi_version() == 7
+    assert lib.amwg_abi_version() == 8
     return pkg
 
 
