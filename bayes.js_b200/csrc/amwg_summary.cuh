@@ -4,9 +4,9 @@
 //
 // Input everywhere: a device-resident sample block in amwg_sample_device's layout, x[row][entry][chain] (chain fastest).
 //   K_m1  amwg_chain_moments_kernel : one thread per (chain, entry): mean and M2 of the chain over its rows, two sequential passes
-//                                     (coalesced over chains; HBM-bound: 2 reads of the block)
-//   K_m2  amwg_merge_moments_kernel : one CTA per entry: Welford/Chan merge of the chain means in a FIXED order (strided
-//                                     per-thread runs, then a shared-memory tree), so the result does not depend on scheduling
+//                                     (coalesced over chains; HBM-bound: 2 reads of the block), Chan-merged per CTA in a fixed tree
+//   K_m2  amwg_merge_moments_kernel : one CTA per entry merges the per-CTA records, again in a FIXED order, so the result does
+//                                     not depend on scheduling
 //   K_q   amwg_digit_hist_kernel    : one pass of an exact MSD radix select over the order-preserving 64-bit key of the draws:
 //                                     counts of the next 8-bit digit among the values whose higher digits equal a given prefix
 //                                     (integer counts: exact, order independent, summed across GPUs by the caller)
@@ -20,22 +20,6 @@ constexpr int kMaxPrefixes = 32;      // distinct prefixes per entry and pass (o
 __device__ __forceinline__ unsigned long long ordered_key(double x) {
   unsigned long long u = (unsigned long long)__double_as_longlong(x);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);      // ascending keys == ascending doubles (-0 < +0, NaN on top)
-}
-
-__global__ void __launch_bounds__(256) amwg_chain_moments_kernel(const double* __restrict__ x, long long rows, int entries, long long C,
-                                                                 double* __restrict__ cmean, double* __restrict__ cm2) {
-  const int e = blockIdx.y;
-  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
-    const double* p = x + (size_t)e * C + c;
-    const size_t stride = (size_t)entries * C;
-    double s = 0.0;
-    for (long long r = 0; r < rows; ++r) s += p[r * stride];
-    const double m = s / (double)rows;
-    double m2 = 0.0;
-    for (long long r = 0; r < rows; ++r) { double d = p[r * stride] - m; m2 = fma(d, d, m2); }
-    cmean[(size_t)e * C + c] = m;
-    cm2[(size_t)e * C + c] = m2;
-  }
 }
 
 struct Moments { double n, mean, m2, sum_w; };     // n chain means merged so far; sum_w = sum of the within-chain M2
@@ -52,23 +36,48 @@ __device__ __forceinline__ Moments merge(const Moments& a, const Moments& b) {
   return r;
 }
 
-// out[entry][4] = {chains, mean of the chain means, M2 of the chain means, sum over chains of the within-chain M2}
-__global__ void __launch_bounds__(1024) amwg_merge_moments_kernel(const double* __restrict__ cmean, const double* __restrict__ cm2, long long C,
-                                                                  double* __restrict__ out) {
-  __shared__ Moments sh[1024];
-  const int e = blockIdx.x, t = threadIdx.x;
-  Moments acc{0.0, 0.0, 0.0, 0.0};
-  for (long long c = t; c < C; c += blockDim.x) {           // fixed order per thread
-    Moments one{1.0, cmean[(size_t)e * C + c], 0.0, cm2[(size_t)e * C + c]};
-    acc = merge(acc, one);
-  }
-  sh[t] = acc;
+template <int THREADS>
+__device__ __forceinline__ Moments cta_merge(Moments* sh, Moments mine) {      // fixed tree: the result does not depend on scheduling
+  const int t = threadIdx.x;
+  sh[t] = mine;
   __syncthreads();
-  for (int w = blockDim.x >> 1; w > 0; w >>= 1) {            // fixed tree
+  for (int w = THREADS >> 1; w > 0; w >>= 1) {
     if (t < w) sh[t] = merge(sh[t], sh[t + w]);
     __syncthreads();
   }
-  if (t == 0) { out[e * 4 + 0] = sh[0].n; out[e * 4 + 1] = sh[0].mean; out[e * 4 + 2] = sh[0].m2; out[e * 4 + 3] = sh[0].sum_w; }
+  return sh[0];
+}
+
+// K_m1: per chain, mean and M2 over its rows (two sequential passes over a coalesced column); the CTA's chains are merged in a
+// fixed order into one record per (entry, CTA).
+__global__ void __launch_bounds__(256) amwg_chain_moments_kernel(const double* __restrict__ x, long long rows, int entries, long long C,
+                                                                 Moments* __restrict__ partial) {
+  __shared__ Moments sh[256];
+  const int e = blockIdx.y;
+  const size_t stride = (size_t)entries * C;
+  Moments acc{0.0, 0.0, 0.0, 0.0};
+  for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
+    const double* p = x + (size_t)e * C + c;
+    double s = 0.0;
+    for (long long r = 0; r < rows; ++r) s += p[r * stride];
+    const double m = s / (double)rows;
+    double m2 = 0.0;
+    for (long long r = 0; r < rows; ++r) { double d = p[r * stride] - m; m2 = fma(d, d, m2); }
+    acc = merge(acc, Moments{1.0, m, 0.0, m2});
+  }
+  const Moments tot = cta_merge<256>(sh, acc);
+  if (threadIdx.x == 0) partial[(size_t)e * gridDim.x + blockIdx.x] = tot;
+}
+
+// K_m2: one CTA per entry merges the per-CTA records. out[entry][4] = {chains, mean of the chain means, M2 of the chain means,
+// sum over chains of the within-chain M2}
+__global__ void __launch_bounds__(1024) amwg_merge_moments_kernel(const Moments* __restrict__ partial, int n_partial, double* __restrict__ out) {
+  __shared__ Moments sh[1024];
+  const int e = blockIdx.x;
+  Moments acc{0.0, 0.0, 0.0, 0.0};
+  for (int i = threadIdx.x; i < n_partial; i += 1024) acc = merge(acc, partial[(size_t)e * n_partial + i]);
+  const Moments tot = cta_merge<1024>(sh, acc);
+  if (threadIdx.x == 0) { out[e * 4 + 0] = tot.n; out[e * 4 + 1] = tot.mean; out[e * 4 + 2] = tot.m2; out[e * 4 + 3] = tot.sum_w; }
 }
 
 // counts[entry][prefix][256] += number of values of `entry` whose key's top 8*pass bits equal prefix[entry][p] and whose next
@@ -86,13 +95,24 @@ __global__ void __launch_bounds__(256) amwg_digit_hist_kernel(const double* __re
   const size_t stride = (size_t)entries * C;
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
     const double* p = x + (size_t)e * C + c;
+    // consecutive rows of one chain mostly fall in the same bin (always, in the leading passes of a narrow posterior): count the
+    // run in a register and touch the shared histogram once per run instead of once per value
+    int last = -1;
+    unsigned int run = 0;
     for (long long r = 0; r < rows; ++r) {
       const unsigned long long k = ordered_key(p[r * stride]);
-      const unsigned int bin = (unsigned int)(k >> shift) & 255u;
-      const unsigned long long hi = pass ? (k >> (shift + 8)) : 0ull;
-      for (int q = 0; q < n_prefix; ++q)
-        if (pass == 0 || hi == pre[q]) atomicAdd(&hist[q * 256 + bin], 1u);
+      int idx = (int)((k >> shift) & 255ull);
+      if (pass) {
+        const unsigned long long hi = k >> (shift + 8);
+        int q = 0;
+        while (q < n_prefix && pre[q] != hi) ++q;           // prefixes are distinct: at most one matches
+        idx = (q < n_prefix) ? q * 256 + idx : -1;
+      }
+      if (idx == last) { ++run; continue; }
+      if (last >= 0) atomicAdd(&hist[last], run);
+      last = idx; run = 1;
     }
+    if (last >= 0) atomicAdd(&hist[last], run);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n_prefix * 256; i += blockDim.x)
@@ -105,19 +125,18 @@ extern "C" int amwg_summary_moments(int device, const double* dev_samples, int64
   if (rows <= 0 || entries <= 0 || chains <= 0) return fail("amwg_summary_moments: empty sample block");
   if (!dev_samples || !host_stats) return fail("amwg_summary_moments: null pointer");
   CUDA_TRY(cudaSetDevice(device));
-  double *cmean = nullptr, *cm2 = nullptr, *d_out = nullptr;
-  const size_t n = (size_t)entries * (size_t)chains;
-  cudaError_t e = cudaMalloc(&cmean, n * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&cm2, n * sizeof(double));
+  const unsigned bx = (unsigned)std::min<int64_t>((chains + 255) / 256, 148 * 8);     // depends on `chains` only: a fixed merge order
+  summary::Moments* partial = nullptr;
+  double* d_out = nullptr;
+  cudaError_t e = cudaMalloc(&partial, (size_t)entries * bx * sizeof(summary::Moments));
   if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)entries * 4 * sizeof(double));
   if (e == cudaSuccess) {
-    const unsigned bx = (unsigned)std::min<int64_t>((chains + 255) / 256, 148 * 8);
-    summary::amwg_chain_moments_kernel<<<dim3(bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, cmean, cm2);
-    summary::amwg_merge_moments_kernel<<<(unsigned)entries, 1024>>>(cmean, cm2, chains, d_out);
+    summary::amwg_chain_moments_kernel<<<dim3(bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, partial);
+    summary::amwg_merge_moments_kernel<<<(unsigned)entries, 1024>>>(partial, (int)bx, d_out);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpy(host_stats, d_out, (size_t)entries * 4 * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(cmean); cudaFree(cm2); cudaFree(d_out);
+  cudaFree(partial); cudaFree(d_out);
   if (e != cudaSuccess) return fail(std::string("amwg_summary_moments: ") + cudaGetErrorString(e));
   return 0;
 }

@@ -34,7 +34,7 @@ def test_summary_matches_numpy_on_the_raw_draws_config2_shape(gpu_pkg):
     data = config2_data().tolist()
     a = mcmc.AmwgSampler(params, models.norm_post_readme(ld), data, {"chains": 4096, "seed": 21})
     b = mcmc.AmwgSampler(params, models.norm_post_readme(ld), data, {"chains": 4096, "seed": 21})
-    a.burn(300); b.burn(300)
+    a.burn(2500); b.burn(2500)
     raw = a.sample(50)
     summ = b.sample_summary(50, PROBS)
     for name in ("mu", "sigma"):
@@ -86,11 +86,13 @@ def test_c_abi_reductions_on_an_adversarial_block(gpu_pkg):
         table, which = sel_d.prefixes()
         cd = red.digit_counts(block, p, table).cpu().numpy()
         ch = ref.digit_counts(torch.from_numpy(x), p, table).numpy()
-        assert np.array_equal(cd, ch), p
+        for e in range(entries):                                # padded repeats of a prefix are not counted by the device
+            assert np.array_equal(cd[e, which[e]], ch[e, which[e]]), (p, e)
         assert cd[:, 0].sum() == entries * rows * chains if p == 0 else True
         sel_d.advance(cd, which); sel_h.advance(ch, which)
     flat = np.sort(np.moveaxis(x, 1, 0).reshape(entries, -1), axis=1)
-    assert np.array_equal(sel_d.values().view(np.uint64), flat[:, ranks].view(np.uint64))
+    assert np.array_equal(sel_d.values(), flat[:, ranks])     # by value: np.sort leaves -0.0 / +0.0 in arbitrary order, the key order is -0 < +0
+    assert np.array_equal(sel_d.values().view(np.uint64), sel_h.values().view(np.uint64))
     fin = np.isfinite(x).all(axis=(0, 2))
     got, want = red.moments(block), ref.moments(torch.from_numpy(x))
     assert np.array_equal(got[:, 0], want[:, 0])
