@@ -60,6 +60,7 @@ struct ModelDev {
   int n_block_params;              // multi-dim parameters stepped with one evaluation (amwg_model.block_params)
   int block_params[AMWG_MAX_BLOCK_PARAMS];
   unsigned off_tbc;                // image offset of term_block_comp [n_block_params][n_terms]
+  int stat_prog;                   // >= 0: sweeps run with pre-evaluated plate statistics (amwg_model.stat_prog), by amwg_stat_sweep_kernel
   const double* col_global[kMaxColumns];
   unsigned col_bytes[kMaxColumns];     // padded to 16
   int col_smem_off[kMaxColumns];       // byte offset in dynamic smem, or -1: read from global/L2
@@ -84,6 +85,7 @@ struct ChainArrays {
   double* tcand;          // [n_terms][C] candidates written while a proposal is evaluated; committed on acceptance
   double* bprop;          // [D][C] block steps: the proposal of every component of the block (its current value when out of bounds)
   double* bcoin;          // [D][C] block steps: the accept uniform drawn for it (-1: proposal out of bounds, no uniform drawn)
+  unsigned short* vseq;   // [D][C] pre-evaluated statistics: the components in this sweep's visiting order
   unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
   unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
   unsigned long long C;
@@ -134,6 +136,7 @@ struct EvalStateT : EvalStateBase {
   using EvalStateBase::EvalStateBase;
   __device__ __forceinline__ void store(int, double) const {}
   __device__ __forceinline__ double cached(int) const { return 0.0; }
+  __device__ __forceinline__ double cand(int) const { return 0.0; }
 };
 template <>
 struct EvalStateT<true> : EvalStateBase {
@@ -150,6 +153,7 @@ struct EvalStateT<true> : EvalStateBase {
   }
   __device__ __forceinline__ void store(int t, double v) const { if (tval) (direct ? tval : tcand)[(unsigned long long)t * tstride] = v; }
   __device__ __forceinline__ double cached(int t) const { return tval[(unsigned long long)t * tstride]; }
+  __device__ __forceinline__ double cand(int t) const { return tcand[(unsigned long long)t * tstride]; }
 };
 using EvalState = EvalStateT<true>;
 
@@ -335,18 +339,22 @@ __device__ __forceinline__ double norm_factorised(const Ctx& ctx, double n, doub
   return n * (ctx.norm_c0 - js_log(sd)) - S / (2 * sd * sd);
 }
 
-__device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean, double sd) {
+// S = sum_i (x_i - mean)^2 of a NORM_IID plate: the O(N) part
+__device__ __forceinline__ double plate_sum_sq(const Ctx& ctx, int q, double mean) {
   const amwg_plate& pl = ctx.plates[q];
   int c = pl.col[0], off = pl.iparam[2];
   unsigned sa = ctx.col_saddr[c] ? ctx.col_saddr[c] + 8u * (unsigned)off : 0u;
   const double* gx = ctx.col[c] + off;
-  double S;
   if (sa == 0u && ctx.ring_saddr && (reinterpret_cast<unsigned long long>(gx) & 15ull) == 0)
-    S = sum_sq_stream(const_cast<Ctx&>(ctx), gx, pl.n, mean);          // column lives in HBM/L2: TMA tile ring
-  else
-    S = sum_sq_dev(gx, sa, pl.n, mean);
-  return norm_factorised(ctx, (double)pl.n, S, sd);
+    return sum_sq_stream(const_cast<Ctx&>(ctx), gx, pl.n, mean);       // column lives in HBM/L2: TMA tile ring
+  return sum_sq_dev(gx, sa, pl.n, mean);
 }
+
+__device__ __noinline__ double plate_norm_iid(const Ctx& ctx, int q, double mean, double sd) {
+  const double S = plate_sum_sq(ctx, q, mean);
+  return norm_factorised(ctx, (double)ctx.plates[q].n, S, sd);
+}
+__device__ __noinline__ double plate_sum_sq_call(const Ctx& ctx, int q, double mean) { return plate_sum_sq(ctx, q, mean); }
 
 // sum_i ld.bern(y_i, p): sequential, bit-faithful to distributions.js:228-230 (x*prob + (1-x)*(1-prob) is exact for x in {0,1}).
 __device__ __noinline__ double plate_bern_iid(const Ctx& ctx, int q, double p, double lp) {
@@ -538,6 +546,15 @@ __device__ __noinline__ double run_program_t(unsigned code_sa, unsigned consts_s
       case AMWG_OP_NORM_K: { double d = x - y; r = z - (d * d) / t; break; }
       case AMWG_OP_UNIF_K: r = (x < y || x > z) ? -CUDART_INF : t; break;
       case AMWG_OP_BETA_K: r = (x > 1 || x < 0) ? -CUDART_INF : (y * js_log(x) + z * js_log(1 - x)) - t; break;
+      case AMWG_OP_PLATE_SS: {               // the plate's statistic at `mean`; also kept in its cache slot (amwg.h stat_prog)
+        const int slot = AMWG_NEXT();
+        r = plate_sum_sq_call(ctx, a, x);
+        es.store(slot, r);
+        break;
+      }
+      case AMWG_OP_NORM_SS: r = norm_factorised(ctx, (double)ctx.plates[a].n, x, y); break;
+      case AMWG_OP_CACHED: r = es.cached(a); break;
+      case AMWG_OP_CAND: r = es.cand(a); break;
       case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
       case AMWG_OP_ACC_RANGE: {              // terms that do not read the moved component: their cached values, one by one, in order
         const int cnt = AMWG_NEXT();
@@ -879,6 +896,129 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
   }
 }
 
+// ---- K1s: sweeps with pre-evaluated plate statistics (amwg_model.stat_prog) ---------------------------------------------
+// Per sweep: (a) every step's proposal and accept uniform, drawn in the chain's visiting order -- the Math.random() calls of
+// mcmc.js:887/246-252 (shuffles) and :519-528 (rnorm trials, one uniform per in-bounds proposal) in their original order, none of
+// which depends on a log_post value; (b) ONE pass over the data: stat_prog evaluates every plate's S at the proposals (all
+// threads of the CTA together: resident columns by broadcast LDS, larger ones through the TMA tile ring); (c) the steps in
+// visiting order, each an O(1) evaluation of comp_prog[c] from cached terms and statistics, accept/reject and commit as
+// mcmc.js:527-534. Same values, sums and uniforms as stepping with the full program -> the same draws, bit for bit.
+__global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+
+  const unsigned long long C = a.C;
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = tid < C;                                   // threads past the last chain shadow chain C-1 and write nothing:
+  const unsigned long long chain = valid ? tid : C - 1;         // they take part in the CTA-wide data pass
+  double* st = a.state + chain;
+  const unsigned long long gchain = a.first_chain + chain;
+
+  RandomStream g;
+  g.init(a.rng_n[chain]);
+  unsigned long long perm = a.perm[chain];
+  double curr = a.curr_lp[chain];
+  const int P = m.n_params, D = m.D;
+  unsigned char order[kMaxDim0];
+
+  long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
+  long long row = sa.record ? (sa.sample_i0 + sa.thin - 1) / sa.thin : 0;
+  for (long long s = 0; s < sa.n_sweeps; ++s) {
+    if (sa.record) {                                            // Sampler.sample: the state BEFORE stepping (mcmc.js:1021-1027)
+      const bool rec_now = rec_phase == 0;
+      if (++rec_phase == sa.thin) rec_phase = 0;
+      if (rec_now && valid) {
+        double der[kMaxDerived];
+        bool have_der = false;
+        for (int j = 0; j < sa.n_monitor; ++j) {
+          int e = sa.monitor[j];
+          double v;
+          if (e < D) {
+            v = st[(unsigned long long)e * C];
+          } else {
+            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_ctx(ctx, es, derived_pc(m, es), der, false); have_der = true; }
+            v = der[e - D];
+          }
+          sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
+        }
+      }
+      if (rec_now) ++row;
+    }
+    // ---- (a) this sweep's random numbers, in the reference's order
+    for (int i = P - 1; i > 0; --i) {                           // shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
+      int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
+      unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
+      perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
+      perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+    }
+    int pos = 0;
+    for (int slot = 0; slot < P; ++slot) {
+      const amwg_param& pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];
+      const int inner = pa.n_comp / pa.dim0;
+      if (pa.n_comp > 1) {                                      // nested_array_random_apply: top level only (mcmc.js:246-252)
+        for (int i = 0; i < pa.dim0; ++i) order[i] = (unsigned char)i;
+        for (int i = pa.dim0 - 1; i > 0; --i) {
+          int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
+          unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
+        }
+      }
+      for (int r = 0; r < pa.n_comp; ++r, ++pos) {
+        int c = pa.comp_offset;
+        if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        const unsigned long long ci = (unsigned long long)c * C + chain;
+        const double cur = a.state[ci];
+        double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci]);          // generate_proposal (mcmc.js:519, 577-579 / 596-598)
+        if (pa.type == AMWG_INT) prop = js_round(prop);
+        const bool inb = !(prop < pa.lower || prop > pa.upper);              // bounds check (:520): no uniform when it fails
+        const double coin = inb ? g.next(a.seed, gchain) : -1.0;
+        if (valid) {
+          a.bprop[ci] = inb ? prop : cur;
+          a.bcoin[ci] = coin;
+          a.vseq[(unsigned long long)pos * C + chain] = (unsigned short)c;
+        }
+      }
+    }
+    // ---- (b) one pass over the data: every plate statistic at the proposals -> candidate slots
+    {
+      EvalState es{st, C, -1, 0.0};
+      es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
+      es.bprop = a.bprop + chain; es.blk_lo = 0; es.blk_hi = D;
+      if (!valid) es.tval = nullptr;                            // shadow threads compute along (barriers) and store nothing
+      eval_logpost<true>(ctx, es, m.stat_prog);
+    }
+    // ---- (c) the steps, in visiting order: O(1) each
+    if (valid) {
+      for (int i = 0; i < D; ++i) {
+        const int c = (int)a.vseq[(unsigned long long)i * C + chain];
+        const unsigned long long ci = (unsigned long long)c * C + chain;
+        const double coin = a.bcoin[ci];
+        if (coin < 0.0) continue;                               // out of bounds: rejected without evaluation (mcmc.js:520-522)
+        const double prop = a.bprop[ci];
+        EvalState es{st, C, c, prop};
+        es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
+        const double lp_new = eval_logpost<true>(ctx, es, ctx.comp_prog[c]);
+        const double accept_prob = js_exp(lp_new - curr);       // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
+        if (accept_prob > coin) {
+          curr = lp_new;
+          a.state[ci] = prop;
+          if (m.adapting[c]) a.acc[ci] += 1;
+          for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
+            const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
+            a.tval[ti] = a.tcand[ti];
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    a.rng_n[chain] = g.n;
+    a.perm[chain] = perm;
+    a.curr_lp[chain] = curr;
+  }
+}
+
 }  // namespace amwg
 #include "amwg_wide.cuh"
 namespace amwg {
@@ -1124,6 +1264,14 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   if (const char* e = getenv("AMWG_BLOCK_STEPS")) { if (atoi(e) == 0) m.n_block_params = 0; }
   for (int k = 0; k < m.n_block_params; ++k) m.block_params[k] = md->block_params[k];
   m.off_tbc = append(md->term_block_comp, m.n_block_params ? sizeof(int32_t) * (size_t)m.n_block_params * (size_t)m.n_terms : 0);
+  // pre-evaluated statistics: comp_prog then reads candidate slots that only amwg_stat_sweep_kernel fills, so switching the
+  // sweep off (AMWG_STAT_SWEEP=0, for A/B runs) also drops the term cache: every step evaluates the full program
+  m.stat_prog = (m.n_terms && md->stat_prog >= 0) ? md->stat_prog : -1;
+  if (md->stat_prog >= 0) {
+    bool off = md->n_variant_comps > 0 || md->n_comp > 65535;
+    if (const char* e = getenv("AMWG_STAT_SWEEP")) off = off || atoi(e) == 0;
+    if (off) { m.stat_prog = -1; m.n_terms = 0; m.n_block_params = 0; }
+  }
   m.image_bytes = (unsigned)image.size();
   unsigned char* d_image = nullptr;
   if (dev_upload(s, image.data(), image.size(), &d_image)) return bail(-1);
@@ -1145,6 +1293,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     }
     m.phase_sync = (all_scalar || md->n_params == 1) ? 1 : 0;
     if (const char* e = getenv("AMWG_PHASE_SYNC")) m.phase_sync = m.phase_sync && atoi(e) != 0;
+    if (m.stat_prog >= 0) m.phase_sync = 1;        // the data pass is CTA-uniform by construction
   }
 
   unsigned smem_used = m.image_bytes;
@@ -1173,6 +1322,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
       cudaFuncSetAttribute(amwg_sweep_kernel_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_stat_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
@@ -1188,7 +1338,9 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
       dev_alloc(s, (size_t)n_chains, &a.perm) || dev_alloc(s, (size_t)n_chains, &a.rng_n))
     return bail(-1);
   a.tval = a.tcand = a.bprop = a.bcoin = nullptr;
-  if (m.n_block_params > 0 && (dev_alloc(s, DC, &a.bprop) || dev_alloc(s, DC, &a.bcoin))) return bail(-1);
+  a.vseq = nullptr;
+  if ((m.n_block_params > 0 || m.stat_prog >= 0) && (dev_alloc(s, DC, &a.bprop) || dev_alloc(s, DC, &a.bcoin))) return bail(-1);
+  if (m.stat_prog >= 0 && dev_alloc(s, DC, &a.vseq)) return bail(-1);
   if (m.n_terms > 0) {
     if (dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tval) || dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tcand)) return bail(-1);
     s->chains_per_thread = 1;            // the experimental wide kernel evaluates the full program only
@@ -1244,7 +1396,8 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       amwg_sweep_kernel_wide<4><<<grid_for((C + 3) / 4, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
     } else {
       const int threads = s->m.phase_sync ? kSyncThreads : kThreads;
-      if (s->m.n_terms > 0) amwg_sweep_kernel<true><<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+      if (s->m.stat_prog >= 0) amwg_stat_sweep_kernel<<<grid_for(C, kSyncThreads), kSyncThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+      else if (s->m.n_terms > 0) amwg_sweep_kernel<true><<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
       else amwg_sweep_kernel<false><<<grid_for(C, threads), threads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
     }
     CUDA_TRY(cudaGetLastError());

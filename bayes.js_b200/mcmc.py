@@ -408,6 +408,8 @@ class AmwgSampler(Sampler):
         m.n_block_params = len(prog.block_params)
         m.block_params = block_params.ctypes.data_as(C.POINTER(C.c_int32)) if prog.block_params else None
         m.term_block_comp = tbc.ctypes.data_as(C.POINTER(C.c_int32)) if prog.block_params else None
+        m.stat_prog = prog.stat_prog
+        m.n_sum_terms = prog.n_sum_terms if prog.stat_prog >= 0 else prog.n_terms
         self._cache_keepalive = (comp_prog, touch_off, touch_terms, block_params, tbc)
         vcomps = np.asarray(prog.variant_comps if prog.variant_comps else [0], dtype=np.int32)
         vlp = np.asarray(prog.variant_logpost if prog.variant_logpost else [0], dtype=np.int32)

@@ -23,6 +23,8 @@ import math
 import numbers
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
+import os
+
 import numpy as np
 
 from ._ffi import (OP, PLATE_BERN_IID, PLATE_GENERIC, PLATE_NORM_GROUPED, PLATE_NORM_IID, PLATE_POIS_LOGLIN)
@@ -297,6 +299,8 @@ _ARITY = {"ADD": 2, "SUB": 2, "MUL": 2, "DIV": 2, "NEG": 1, "LOG": 1, "EXP": 1, 
           "LD_NORM": 3, "LD_UNIF": 3, "LD_BETA": 3, "LD_BERN": 2, "LD_POIS": 2, "LD_CAUCHY": 3, "LD_LAPLACE": 3,
           "LD_GAMMA": 3, "LD_INVGAMMA": 3, "LD_LNORM": 3, "LD_PARETO": 3, "LD_T": 4, "LD_WEIBULL": 3, "LD_LOGIS": 3,
           "LD_EXP": 2, "LD_BINOM": 3, "LD_NBINOM": 3, "LD_HYPER": 4, "NORM_K": 4, "UNIF_K": 4, "BETA_K": 4}
+ACC_FLAG = 1 << 16
+MIN_STAT_POINTS = 64    # pre-evaluated statistics pay for their bookkeeping from about this many plate points
 
 
 class Program:
@@ -316,6 +320,8 @@ class Program:
         self.comp_prog: List[int] = []
         self.touch_off: List[int] = []
         self.touch_terms: List[int] = []
+        self.stat_prog = -1                    # pre-evaluated plate statistics (amwg.h stat_prog): -1 = not in use
+        self.n_sum_terms = 0                   # ... terms of the sum; slots n_sum_terms .. n_terms-1 of the term cache hold the statistics
         self.block_params: List[int] = []      # parameters stepped with one evaluation (amwg.h block_params) ...
         self.term_block_comp: List[int] = []   # ... and, per such parameter, the component of it each term reads (-1: none)
         self.variant_comps: List[int] = []     # binary components whose configuration selects the program (amwg.h variant_*)
@@ -569,6 +575,7 @@ class Lowering:
         self._terms: List[dict] = []             # top-level terms of the (single) log_post program: start, end, kind, deps, cost
         self._abs_words: List[int] = []          # positions of words that hold absolute program offsets (loop targets)
         self._record_terms = False
+        self._stat_mode = False                  # second lowering pass: NORM_IID plates as PLATE_SS + NORM_SS (amwg.h stat_prog)
 
     # -- constant folding ---------------------------------------------------------------------------
     def _key(self, n: Sym):
@@ -715,6 +722,19 @@ class Lowering:
                 p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
         p.plates.append(pl)
         start = len(p.code)
+        if pl["kind"] == PLATE_NORM_IID and self._stat_mode:
+            # the O(N) statistic S(mean) and the O(1) combination f(S, sd) as two instructions, S kept in its own cache slot
+            mean_p, sd_p = self.prepared(operands[0]), self.prepared(operands[1])
+            k = sum(1 for tr in self._terms if tr.get("stat") is not None)
+            modes, words = self._operands([mean_p])
+            ss_word = len(p.code)
+            p.emit("PLATE_SS", q, *words, -1 - k, modes=modes)          # slot patched once the number of terms is known
+            split = len(p.code)
+            m_sd, w_sd = self._operands([sd_p])
+            p.emit("NORM_SS", q, *w_sd, modes=[MODE_STACK] + m_sd, acc=True, store=len(self._terms))
+            self._terms.append(dict(start=start, end=len(p.code), kind="value", deps=self._deps(mean_p) | self._deps(sd_p), cost=3 * n,
+                                    stat=dict(k=k, ss_word=ss_word, slot_word=split - 1, split=split, mean_deps=self._deps(mean_p), n=n)))
+            return
         if pl["kind"] != PLATE_GENERIC:
             prepared = [self.prepared(o) for o in operands]
             modes, words = self._operands(prepared)
@@ -727,7 +747,8 @@ class Lowering:
                     deps |= self._deps(o)
                 if pl["kind"] == PLATE_NORM_GROUPED or pl["kind"] == PLATE_POIS_LOGLIN:
                     deps |= set(range(pl["iparam"][0], pl["iparam"][0] + pl["iparam"][1]))
-                self._terms.append(dict(start=start, end=len(p.code), kind="value" if value_plate else "inorder", deps=deps, cost=3 * n))
+                self._terms.append(dict(start=start, end=len(p.code), kind="value" if value_plate else "inorder", deps=deps, cost=3 * n,
+                                        plate_kind=pl["kind"], mean_deps=self._deps(prepared[0]) if pl["kind"] == PLATE_NORM_IID else None, n=n))
             return
         # generic: a bytecode loop, lp += body(i) in order
         p.emit("LOOP_BEGIN", q, 0)
@@ -739,7 +760,8 @@ class Lowering:
         self._abs_words.append(len(p.code) - 1)
         p.code[fix] = len(p.code)
         if self._record_terms:
-            self._terms.append(dict(start=start, end=len(p.code), kind="inorder", deps=set(), cost=12 * n * max(1, len(p.code) - body_start)))
+            self._terms.append(dict(start=start, end=len(p.code), kind="inorder", deps=set(), cost=12 * n * max(1, len(p.code) - body_start),
+                                    plate_kind=PLATE_GENERIC))
         p.summary.append(f"plate GENERIC n={n} body={body.op}")
 
     def _grouped(self, mean: Sym, n: int):
@@ -912,9 +934,86 @@ class Lowering:
         p.store_sites = []
         return shift(der_off) if der_off >= 0 else der_off
 
+    def _stat_mode_applies(self) -> bool:
+        """amwg.h stat_prog: every O(N) piece of log_post is a NORM_IID plate whose mean reads exactly one component; no binary
+        parameter; enough plate points for one data pass per sweep (instead of one per step) to matter."""
+        terms = self._terms
+        plates = [tr for tr in terms if "plate_kind" in tr]
+        if os.environ.get("AMWG_STAT_LOWERING", "1") == "0":          # A/B runs and the tests of the other evaluation modes
+            return False
+        if not plates or any(ptype == "binary" for _, _, ptype in self.param_ranges) or not self.param_ranges:
+            return False
+        if any(tr["plate_kind"] != PLATE_NORM_IID or len(tr["mean_deps"]) != 1 for tr in plates):
+            return False
+        if any(tr["kind"] != "value" for tr in terms) or len(terms) + len(plates) > MAX_IMMEDIATE:
+            return False
+        return sum(tr["n"] for tr in plates) >= MIN_STAT_POINTS
+
+    def _emit_stat_programs(self):
+        """comp_prog[c] without O(N) work + stat_prog (amwg.h stat_prog). Called after the stat-mode pass over log_post."""
+        p, terms = self.prog, self._terms
+        n_sum = len(terms)
+        stats = [tr["stat"] for tr in terms if tr.get("stat") is not None]
+        for st in stats:                                             # statistics live behind the terms of the sum
+            st["slot"] = n_sum + st["k"]
+            p.code[st["slot_word"]] = st["slot"]
+        p.n_sum_terms, p.n_terms = n_sum, n_sum + len(stats)
+        for c in range(self.n_comp):
+            p.comp_prog.append(len(p.code))
+            p.touch_off.append(len(p.touch_terms))
+            run_start, run_len = None, 0
+            for t, tr in enumerate(terms):
+                if c not in tr["deps"]:
+                    if run_len and run_start + run_len == t:
+                        run_len += 1
+                    else:
+                        if run_len:
+                            p.emit("ACC_RANGE", run_start, run_len)
+                        run_start, run_len = t, 1
+                    continue
+                if run_len:
+                    p.emit("ACC_RANGE", run_start, run_len)
+                run_start, run_len = None, 0
+                st = tr.get("stat")
+                if st is None:
+                    p.code.extend(p.code[tr["start"]:tr["end"]])
+                else:                                                # the plate's S: pre-evaluated at the proposal, or the committed one
+                    moved_mean = c in st["mean_deps"]
+                    p.emit("CAND" if moved_mean else "CACHED", st["slot"])
+                    p.code.extend(p.code[st["split"]:tr["end"]])
+                    if moved_mean:
+                        p.touch_terms.append(st["slot"])
+                p.touch_terms.append(t)
+            if run_len:
+                p.emit("ACC_RANGE", run_start, run_len)
+            p.emit("END")
+        p.touch_off.append(len(p.touch_terms))
+        p.stat_prog = len(p.code)
+        for tr in terms:
+            st = tr.get("stat")
+            if st is not None:
+                frag = list(p.code[tr["start"]:st["split"]])
+                frag[st["ss_word"] - tr["start"]] |= ACC_FLAG            # nothing consumes S here: do not leave it on the stack
+                p.code.extend(frag)
+        p.emit("END")
+        p.summary.append(f"pre-evaluated statistics: {len(stats)} plate(s), {sum(st['n'] for st in stats)} points, one data pass per sweep")
+
     def lower(self, result: Sym, derived: Dict[str, Sym]) -> Program:
         self._record_terms = True
+        p = self.prog
+        mark = (len(p.code), len(p.plates), len(p.summary), len(p.store_sites), len(self._abs_words))
         lp_off, der_off = self.add_logpost(result, derived)
+        if not self.faithful and self._stat_mode_applies():
+            # lower log_post again with the plates split into statistic + combination (same plates, same fold slots and constants)
+            del p.code[mark[0]:], p.plates[mark[1]:], p.summary[mark[2]:], p.store_sites[mark[3]:], self._abs_words[mark[4]:]
+            self._terms = []
+            self._stat_mode = True
+            lp_off, der_off = self.add_logpost(result, derived)
+            self._stat_mode = False
+            self._record_terms = False
+            self._emit_stat_programs()
+            p.logpost_prog, p.derived_prog = lp_off, der_off
+            return self.finish()
         self._record_terms = False
         if self._cache_worthwhile():
             self._emit_component_programs()

@@ -123,6 +123,12 @@ enum {
   AMWG_OP_BETA_K,       /* (x, a1, b1, K):    (x>1 || x<0) ? -inf : a1*log(x) + b1*log(1-x) - K, a1 = shape1-1, b1 = shape2-1, K = lbeta (:104-113) */
   AMWG_OP_ACC_RANGE,    /* lp = lp + cache[a] + cache[a+1] + ... (next word: count), one term at a time, in order: the terms of the
                            sum that do not read the moved component, taken from the chain's term cache (see amwg_model.comp_prog) */
+  /* Pre-evaluated plate statistics (see amwg_model.stat_prog). A NORM_IID plate is  f(S, sd) = n*(-0.5*log(2pi) - log(sd)) - S/(2*sd*sd)
+   * with S = sum_i (x_i - mean)^2 -- the O(N) part, which only depends on the mean operand. */
+  AMWG_OP_PLATE_SS,     /* (mean): push S of plate `a`; next word: the statistic's slot in the term cache, S is stored there too */
+  AMWG_OP_NORM_SS,      /* (S, sd): f(S, sd) of plate `a` (same operations as AMWG_PLATE_NORM_IID, given its S)                */
+  AMWG_OP_CACHED,       /* push cache[a]      : the committed value of slot a (a statistic of the chain's current state)       */
+  AMWG_OP_CAND,         /* push candidate[a]  : the value the last stat_prog evaluation computed for slot a (at the proposals)   */
   AMWG_OP__COUNT
 };
 
@@ -184,6 +190,17 @@ typedef struct {
    * one. block_params lists such parameters (indices into params[]); term_block_comp[k * n_terms + t] is the component of
    * block_params[k] that term t reads, or -1. */
   int32_t n_block_params;   const int32_t* block_params;   const int32_t* term_block_comp;
+  /* Pre-evaluated statistics (optional, needs comp_prog; no binary parameter, no variants). When every O(N) plate is a NORM_IID
+   * plate whose mean reads exactly ONE component, the expensive part of a proposal's evaluation -- S at the proposed value of that
+   * component -- does not depend on how the other steps of the sweep turn out, and neither do the sweep's random numbers (a step
+   * consumes its rnorm trials and, if the proposal is in bounds, one uniform, whatever log_post says: mcmc.js:519-528). So a sweep
+   * is run as: (a) draw every step's proposal and accept uniform, in the chain's visiting order; (b) ONE pass over the data:
+   * stat_prog evaluates every statistic at the proposals (candidate slots n_sum_terms .. n_terms-1 of the term cache);
+   * (c) the steps, in visiting order, each with comp_prog[c] -- which now contains no O(N) work: a plate term is NORM_SS of
+   * CAND(slot) (the moved component is the plate's mean) or CACHED(slot) (it is not). Same values, same sums, same uniforms as
+   * stepping with the full program, at one data pass per sweep instead of one per step. The term cache then has n_terms slots of
+   * which the first n_sum_terms are terms of the sum (ACC_RANGE only ever covers those); without stat_prog n_sum_terms == n_terms. */
+  int32_t stat_prog;        int32_t n_sum_terms;           /* stat_prog: word offset, -1 = not in use */
   int32_t n_variant_comps;  const int32_t* variant_comps;
   const int32_t* variant_logpost;  const int32_t* variant_derived;     /* 1 << n_variant_comps entries each (derived: -1 if none) */
 } amwg_model;

@@ -23,15 +23,17 @@ def fold_constants(prog, O):
     return consts
 
 
-def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0, cache=None, cand=None):
+def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0, cache=None, cand=None, props=None):
     """`cache` / `cand`: the chain's term cache (list of n_terms values) and where STORE writes (cand, or the cache itself when
-    cand is None) -- mirrors EvalState.tval / tcand / direct."""
+    cand is None) -- mirrors EvalState.tval / tcand / direct. `props`: every component at its proposal (stat_prog's evaluation)."""
     code, cols, plates = prog.code, prog.columns, prog.plates
     stk = []
     lp = 0.0
     li = ln = 0
 
     def comp(c):
+        if props is not None:
+            return float(props[c])
         return val if c == moved else float(state[c])
 
     def nxt():
@@ -94,6 +96,18 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0,
             n = {"LD_BERN": 2, "LD_POIS": 2, "LD_EXP": 2, "LD_T": 4, "LD_HYPER": 4}.get(op, 3)
             args = [opnd(m) for m in (mA, mB, mC, mD)[:n][::-1]][::-1]
             r = _ld(O, op[3:].lower(), *args)
+        elif op == "PLATE_SS":
+            mean = opnd(mA); slot = nxt()
+            pl = plates[a]
+            x = np.asarray(cols[pl["col"][0]][pl["iparam"][2]:pl["iparam"][2] + pl["n"]], dtype=np.float64)
+            r = float(np.sum((x - mean) ** 2))
+            if cache is not None:
+                (cand if cand is not None else cache)[slot] = r
+        elif op == "NORM_SS":
+            sd = opnd(mB); S = opnd(mA)
+            r = plates[a]["n"] * (-0.5 * O.orc_log(2 * JS_PI) - O.orc_log(sd)) - S / (2 * sd * sd)
+        elif op == "CACHED": r = cache[a]
+        elif op == "CAND": r = cand[a]
         elif op == "ACC": lp = lp + stk.pop()
         elif op == "ACC_RANGE":
             cnt = nxt()

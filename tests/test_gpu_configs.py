@@ -83,7 +83,7 @@ def test_config4_hierarchical_normal(gpu_pkg, orc):
     # fast path (one factorised plate per group): same posterior
     s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 4096, "seed": 6})
     assert [x for x in s.program_summary() if x.startswith("plate")] == [f"plate NORM_IID n={per}"] * J
-    assert any(x.startswith("dependency-aware evaluation") for x in s.program_summary())
+    assert any(x.startswith("pre-evaluated statistics") for x in s.program_summary())
     s.burn(1500)
     fast = s.sample(1)
     ref = orc.run_model("hier_norm", {"y": y, "g": g}, params, chains=1024, seed=6, burn=1500, sample=1)
@@ -94,55 +94,88 @@ def test_config4_hierarchical_normal(gpu_pkg, orc):
     assert stats.ks_2samp(fast["sigma"].reshape(-1), ref["sigma"].reshape(-1)).statistic < 0.06
 
 
-def test_dependency_aware_evaluation_is_bit_identical_to_the_full_program(gpu_pkg):
-    """config-4 shape: a step on mu_j recomputes only prior_j and group j's plate, the rest comes from the per-chain term cache.
-    The cached terms are added in their original positions, so every draw equals the run that evaluates the full program."""
+MODES = (("stat", {}),                                                     # pre-evaluated statistics: one data pass per sweep
+         ("full", {"AMWG_STAT_SWEEP": "0"}),                               # same programs, every step evaluates the full one
+         ("block", {"AMWG_STAT_LOWERING": "0"}),                           # block step for mu (one evaluation), term cache
+         ("cache", {"AMWG_STAT_LOWERING": "0", "AMWG_BLOCK_STEPS": "0"}),   # per-component programs with the term cache
+         ("plain", {"AMWG_STAT_LOWERING": "0", "AMWG_TERM_CACHE": "0"}),   # the plain full program with single-op plates
+         ("block_l2", {"AMWG_STAT_LOWERING": "0", "AMWG_PHASE_SYNC": "0"}))
+
+
+def _run_modes(gpu_pkg, modes, make, burn, sample):
     import os
+    out = {}
+    for name, env in modes:
+        os.environ.update(env)
+        try:
+            s = make()
+            out[name + "_summary"] = s.program_summary()
+            s.burn(burn)
+            out[name] = s.sample(sample)
+            out[name + "_info"] = s.info()["steppers"][0]
+            out[name + "_state"] = s.state
+        finally:
+            for k in env:
+                del os.environ[k]
+    return out
+
+
+def test_evaluation_modes_are_bit_identical(gpu_pkg):
+    """config-4 shape. However the work is organised -- one data pass per sweep with pre-evaluated statistics, one evaluation per
+    block, per-component programs over the term cache, or the full program at every step -- the terms are the same values added in
+    the same order and the uniforms are consumed in the same order: every draw is identical."""
     J, per = 8, 32
     y, g, params = _hier(J, per, 65)
     data = {"y": y.tolist(), "g": g.tolist()}
     mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
-    out = {}
-    for name, env in (("block", {}), ("cache", {"AMWG_BLOCK_STEPS": "0"}), ("full", {"AMWG_TERM_CACHE": "0"}), ("block_l2", {"AMWG_PHASE_SYNC": "0"})):
-        os.environ.update(env)
-        try:
-            s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 512, "seed": 12})
-            if name == "block":
-                assert any(x.startswith("block steps") for x in s.program_summary())
-            s.burn(120)
-            out[name] = s.sample(60)
-            out[name + "_info"] = s.info()["steppers"][0]
-        finally:
-            for k in env:
-                del os.environ[k]
-    # block steps (all J group means with one evaluation), per-component cached programs, and the plain full program: same draws
-    for other in ("cache", "full", "block_l2"):
-        assert np.array_equal(out["block"]["mu"], out[other]["mu"]) and np.array_equal(out["block"]["sigma"], out[other]["sigma"]), other
-        assert np.array_equal(out["block_info"]["mu"]["prop_log_scale"], out[other + "_info"]["mu"]["prop_log_scale"])
-    assert out["block"]["mu"].std() > 0
+    out = _run_modes(gpu_pkg, MODES, lambda: mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 500, "seed": 12}), 120, 60)
+    assert any(x.startswith("pre-evaluated statistics: 8 plate(s), 256 points") for x in out["stat_summary"])
+    assert any(x.startswith("block steps") for x in out["block_summary"])
+    for other in [m for m, _ in MODES[1:]]:
+        assert np.array_equal(out["stat"]["mu"], out[other]["mu"]) and np.array_equal(out["stat"]["sigma"], out[other]["sigma"]), other
+        assert np.array_equal(out["stat_info"]["mu"]["prop_log_scale"], out[other + "_info"]["mu"]["prop_log_scale"]), other
+        assert np.array_equal(out["stat_info"]["sigma"]["acceptance_count"], out[other + "_info"]["sigma"]["acceptance_count"]), other
+    assert out["stat"]["mu"].std() > 0
 
 
-def test_block_steps_stream_the_data_through_the_tile_ring(gpu_pkg):
-    """config-4 shape with data that does not fit in shared memory (8 groups x 4096 points = 256 KB + the group column): with
-    block steps every chain takes one evaluation per sweep slot, so the CTA walks the plates together and the column goes through
-    the TMA tile ring; one tile per group here, so the sums are the same as on the L2 path -- identical draws."""
-    import os
+def test_statistics_sweep_on_the_headline_shape_with_int_bounds_thin_and_derived(gpu_pkg):
+    """config-2 shape (two scalar parameters, N=1024, sigma bounded below: out-of-bounds proposals draw no uniform), an int mean
+    (Math.round proposals), thinning, a derived quantity and a chain count that leaves the last CTA ragged."""
+    import models
+    from conftest import config2_data
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    data = config2_data().tolist()
+    two = (("stat", {}), ("full", {"AMWG_STAT_SWEEP": "0"}), ("plain", {"AMWG_STAT_LOWERING": "0"}))
+    pars = {"mu": {"type": "real"}, "sigma": {"type": "real", "lower": 0}}
+    out = _run_modes(gpu_pkg, two, lambda: mcmc.AmwgSampler(pars, models.norm_post_test(ld), data, {"chains": 1000, "seed": 3, "thin": 3}), 230, 100)
+    assert out["stat"]["mu"].shape == (34, 1000) and set(out["stat"]) == {"mu", "sigma", "var"}
+    for other in ("full", "plain"):
+        for k in ("mu", "sigma", "var"):
+            assert np.array_equal(out["stat"][k], out[other][k]), (other, k)
+        assert np.array_equal(out["stat_state"]["var"], out[other + "_state"]["var"])
+        assert np.array_equal(out["stat_info"]["sigma"]["prop_log_scale"], out[other + "_info"]["sigma"]["prop_log_scale"])
+    assert abs(out["stat_state"]["mu"].mean() - np.mean(data)) < 3
+    pars = {"mu": {"type": "int", "lower": 150, "upper": 200, "init": 170}, "sigma": {"type": "real", "lower": 0, "upper": 50}}
+    out = _run_modes(gpu_pkg, two, lambda: mcmc.AmwgSampler(pars, models.norm_post_readme(ld), data, {"chains": 333, "seed": 4}), 150, 80)
+    for other in ("full", "plain"):
+        assert np.array_equal(out["stat"]["mu"], out[other]["mu"]) and np.array_equal(out["stat"]["sigma"], out[other]["sigma"]), other
+    assert np.all(out["stat"]["mu"] == np.round(out["stat"]["mu"])) and out["stat"]["mu"].std() > 0
+
+
+def test_data_larger_than_shared_memory_streams_through_the_tile_ring(gpu_pkg):
+    """config-4 shape with data that does not fit in shared memory (8 groups x 4096 points = 256 KB): the sweep's single data pass
+    (pre-evaluated statistics) and the block step's single evaluation are CTA-uniform, so the column goes through the TMA tile ring;
+    one tile per group here, so the sums are the same as on the L2 path -- identical draws."""
     J, per = 8, 4096
     y, g, params = _hier(J, per, 66)
     data = {"y": y.tolist(), "g": g.tolist()}
     mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
-    out = {}
-    for name, env in (("ring", {}), ("l2", {"AMWG_PHASE_SYNC": "0"})):
-        os.environ.update(env)
-        try:
-            s = mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 256, "seed": 13})
-            s.burn(60)
-            out[name] = s.sample(20)
-        finally:
-            for k in env:
-                del os.environ[k]
-    assert np.array_equal(out["ring"]["mu"], out["l2"]["mu"]) and np.array_equal(out["ring"]["sigma"], out["l2"]["sigma"])
-    assert np.isfinite(out["ring"]["mu"]).all() and out["ring"]["mu"].std() > 0 and out["ring"]["sigma"].std() > 0
+    modes = (("stat_ring", {}), ("full_l2", {"AMWG_STAT_SWEEP": "0", "AMWG_PHASE_SYNC": "0"}),
+             ("block_ring", {"AMWG_STAT_LOWERING": "0"}), ("block_l2", {"AMWG_STAT_LOWERING": "0", "AMWG_PHASE_SYNC": "0"}))
+    out = _run_modes(gpu_pkg, modes, lambda: mcmc.AmwgSampler(params, hier_post(ld, J), data, {"chains": 256, "seed": 13}), 60, 20)
+    for other in ("full_l2", "block_ring", "block_l2"):
+        assert np.array_equal(out["stat_ring"]["mu"], out[other]["mu"]) and np.array_equal(out["stat_ring"]["sigma"], out[other]["sigma"]), other
+    assert np.isfinite(out["stat_ring"]["mu"]).all() and out["stat_ring"]["mu"].std() > 0 and out["stat_ring"]["sigma"].std() > 0
 
 
 def poisreg_post(ld, mcmc, K):

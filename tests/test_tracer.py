@@ -32,7 +32,8 @@ def _oracle_logpost(orc, model, data, params, state):
 
 def test_normal_model_becomes_two_terms_and_a_plate(pkg, orc):
     prog, derived, n = _trace(pkg, models.norm_post_test(pkg.ld), models.PARAMS1, config2_data().tolist())
-    assert prog.summary == ["term LD_NORM", "term LD_UNIF", "plate NORM_IID n=1024"]
+    assert prog.summary == ["term LD_NORM", "term LD_UNIF", "plate NORM_IID n=1024",
+                            "pre-evaluated statistics: 1 plate(s), 1024 points, one data pass per sweep"]
     assert derived == ["var"] and n == 2
     assert len(prog.fold_prog) >= 3                    # log(2pi)-log(100), 2*100*100, log(1/(100-0)) are computed once
     consts = prog_eval.fold_constants(prog, orc.lib())
@@ -114,7 +115,7 @@ def test_symbolic_index_gives_the_same_program_as_the_concrete_loop(pkg):
 def test_hierarchical_and_regression_plates(pkg, orc):
     ld, mcmc = pkg.ld, pkg.mcmc
     rng = np.random.default_rng(2)
-    J, per = 4, 16
+    J, per = 4, 8                                  # 32 plate points: below tracer.MIN_STAT_POINTS, so the plates stay single terms
     g = np.repeat(np.arange(J), per)
     y = rng.normal(100, 20, J)[g] + rng.normal(0, 5, J * per)
 
@@ -177,6 +178,61 @@ def test_hierarchical_and_regression_plates(pkg, orc):
     st = list(rng.normal(0, 0.3, K))
     ref, _ = _oracle_logpost(orc, "pois_reg", {"y": yy, "X": X}, params, st)
     assert abs(prog_eval.logpost(prog, consts, st, orc.lib()) - ref) <= 1e-11 * abs(ref)
+
+
+def test_pre_evaluated_statistics_programs(pkg, orc):
+    """amwg.h stat_prog: NORM_IID plates whose mean reads one component are split into S (one data pass per sweep, at every
+    component's proposal) and f(S, sd); the per-component programs then hold no O(N) work and still give the full program's value."""
+    ld = pkg.ld
+    rng = np.random.default_rng(3)
+    J, per = 4, 16
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(100, 20, J)[g] + rng.normal(0, 5, J * per)
+
+    def hier(state, d):
+        lp = 0
+        for j in range(J):
+            lp += ld.norm(state.mu[j], 0, 100)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]] * 1.0, state.sigma * 1.0)     # operands that are expressions, not bare components
+        return lp
+    params = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
+    prog, _, D = _trace(pkg, hier, params, {"y": y.tolist(), "g": g.tolist()})
+    assert prog.summary[-1].startswith("pre-evaluated statistics: 4 plate(s), 64 points")
+    assert prog.stat_prog >= 0 and prog.n_sum_terms == 2 * J + 1 and prog.n_terms == 3 * J + 1 and not prog.block_params
+    assert [prog.touch_off[c + 1] - prog.touch_off[c] for c in range(D)] == [3] * J + [J + 1]
+    O = orc.lib()
+    consts = prog_eval.fold_constants(prog, O)
+    st = list(rng.normal(100, 20, J)) + [4.0]
+    ref, _ = _oracle_logpost(orc, "hier_norm", {"y": y, "g": g}, params, st)
+    cache = [None] * prog.n_terms
+    full0 = prog_eval.run(prog, consts, st, prog.logpost_prog, O, cache=cache)            # fills terms AND statistics
+    assert None not in cache and abs(full0 - ref) <= 1e-12 * abs(ref)
+    for sweep in range(25):
+        props = [st[c] + rng.normal(0, 0.5) if c < J else abs(st[c] + rng.normal(0, 0.3)) for c in range(D)]
+        cand = list(cache)
+        prog_eval.run(prog, consts, st, prog.stat_prog, O, cache=cache, cand=cand, props=props)       # (b) one data pass
+        for c in rng.permutation(D):                                                                   # (c) the steps, in any order
+            c = int(c)
+            fast = prog_eval.run(prog, consts, st, prog.comp_prog[c], O, moved=c, val=props[c], cache=cache, cand=cand)
+            slow = prog_eval.run(prog, consts, st, prog.logpost_prog, O, moved=c, val=props[c])
+            assert fast == slow, (sweep, c)
+            if rng.random() < 0.5:
+                st[c] = props[c]
+                for k in range(prog.touch_off[c], prog.touch_off[c + 1]):
+                    cache[prog.touch_terms[k]] = cand[prog.touch_terms[k]]
+    # config-2 shape: both parameters scalar, the plate's mean is mu
+    prog, _, _ = _trace(pkg, models.norm_post_readme(ld), models.PARAMS1, config2_data().tolist())
+    assert prog.stat_prog >= 0 and prog.n_sum_terms == 3 and prog.n_terms == 4
+    assert list(prog.touch_terms[prog.touch_off[0]:prog.touch_off[1]]) == [0, 3, 2] and list(prog.touch_terms[prog.touch_off[1]:prog.touch_off[2]]) == [1, 2]
+    # a mean that reads two components cannot be pre-evaluated; neither can a model with a binary parameter; `faithful` keeps the JS loop
+    two = lambda s, d: sum((ld.norm(d[i], s.a + s.b, 1.0) for i in range(len(d))), 0)
+    prog, _, _ = _trace(pkg, two, {"a": {"type": "real"}, "b": {"type": "real"}}, list(range(100)))
+    assert prog.stat_prog == -1
+    prog, _, _ = _trace(pkg, models.spike_bern(ld, pkg.mcmc), {"theta": {"type": "real", "lower": 0, "upper": 1}, "m": {"type": "binary"}},
+                        {"x": [1.0, 0.0] * 64})
+    assert prog.stat_prog == -1
 
 
 def test_control_flow_on_binary_parameters_is_recorded_per_configuration(pkg, orc):
