@@ -61,6 +61,8 @@ struct ModelDev {
   int block_params[AMWG_MAX_BLOCK_PARAMS];
   unsigned off_tbc;                // image offset of term_block_comp [n_block_params][n_terms]
   int stat_prog;                   // >= 0: sweeps run with pre-evaluated plate statistics (amwg_model.stat_prog), by amwg_stat_sweep_kernel
+  int stat_barriers;               // CTA barriers between the phases of a statistics sweep (instruction-cache locality)
+  int scratch_smem_off;            // >= 0: byte offset in dynamic smem of the CTA's per-chain working set (amwg_stat_sweep_kernel), -1: global rows
   const double* col_global[kMaxColumns];
   unsigned col_bytes[kMaxColumns];     // padded to 16
   int col_smem_off[kMaxColumns];       // byte offset in dynamic smem, or -1: read from global/L2
@@ -558,7 +560,13 @@ __device__ __noinline__ double run_program_t(unsigned code_sa, unsigned consts_s
       case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
       case AMWG_OP_ACC_RANGE: {              // terms that do not read the moved component: their cached values, one by one, in order
         const int cnt = AMWG_NEXT();
-        for (int k = 0; k < cnt; ++k) lp = lp + es.cached(a + k);
+        int k = 0;
+        for (; k + 8 <= cnt; k += 8) {       // the loads first (independent, eight in flight), then the adds in order
+          const double v0 = es.cached(a + k), v1 = es.cached(a + k + 1), v2 = es.cached(a + k + 2), v3 = es.cached(a + k + 3);
+          const double v4 = es.cached(a + k + 4), v5 = es.cached(a + k + 5), v6 = es.cached(a + k + 6), v7 = es.cached(a + k + 7);
+          lp = lp + v0; lp = lp + v1; lp = lp + v2; lp = lp + v3; lp = lp + v4; lp = lp + v5; lp = lp + v6; lp = lp + v7;
+        }
+        for (; k < cnt; ++k) lp = lp + es.cached(a + k);
         has_r = false;
         break;
       }
@@ -838,7 +846,17 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
             const double coin = a.bcoin[cqi];
             if (coin < 0.0) continue;                        // out of bounds: rejected without evaluation (mcmc.js:520-522)
             double lpq = 0.0;
-            for (int t = 0; t < m.n_terms; ++t) {
+            int t = 0;
+            for (; t + 4 <= m.n_terms; t += 4) {             // loads first (four in flight), adds in order
+              double v[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const unsigned long long ti = (unsigned long long)(t + u) * C + chain;
+                v[u] = (tbc[t + u] == cq ? a.tcand : a.tval)[ti];
+              }
+              lpq = lpq + v[0]; lpq = lpq + v[1]; lpq = lpq + v[2]; lpq = lpq + v[3];
+            }
+            for (; t < m.n_terms; ++t) {
               const unsigned long long ti = (unsigned long long)t * C + chain;
               lpq = lpq + (tbc[t] == cq ? a.tcand[ti] : a.tval[ti]);
             }
@@ -903,6 +921,12 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
 // threads of the CTA together: resident columns by broadcast LDS, larger ones through the TMA tile ring); (c) the steps in
 // visiting order, each an O(1) evaluation of comp_prog[c] from cached terms and statistics, accept/reject and commit as
 // mcmc.js:527-534. Same values, sums and uniforms as stepping with the full program -> the same draws, bit for bit.
+//
+// Per-chain working set: rows [tval n_terms | tcand n_terms | bprop D | bcoin D | state D] of doubles + vseq D of u16. When it
+// fits beside the model and the data (scratch_smem_off >= 0: small models, e.g. the headline one) it lives in SHARED memory for
+// the whole launch, one column per thread (row stride = CTA size, conflict-free): state and term cache are read from HBM once
+// per launch and written back once, the per-sweep temporaries never leave the SM. Otherwise the rows are the global arrays
+// (row stride = C), which amwg_create lays out back to back in the same order.
 __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_kernel(ModelDev m, ChainArrays a, SweepArgs sa) {
   extern __shared__ __align__(16) unsigned char smem[];
   __shared__ Ctx ctx;
@@ -912,15 +936,27 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
   const unsigned long long C = a.C;
   const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = tid < C;                                   // threads past the last chain shadow chain C-1 and write nothing:
-  const unsigned long long chain = valid ? tid : C - 1;         // they take part in the CTA-wide data pass
-  double* st = a.state + chain;
+  const unsigned long long chain = valid ? tid : C - 1;         // they take part in the CTA-wide data pass and the barriers
   const unsigned long long gchain = a.first_chain + chain;
+  const int P = m.n_params, D = m.D, NT = m.n_terms;
+  const bool in_smem = m.scratch_smem_off >= 0;
+  // rows of the working set: wk[row * ws]; state rows: sp[c * ss]
+  double* wk = in_smem ? reinterpret_cast<double*>(smem + m.scratch_smem_off) + threadIdx.x : a.tval + chain;
+  const unsigned long long ws = in_smem ? (unsigned long long)kSyncThreads : C;
+  double* sp = in_smem ? wk + (unsigned long long)(2 * NT + 2 * D) * ws : a.state + chain;
+  unsigned short* vq = in_smem ? reinterpret_cast<unsigned short*>(smem + m.scratch_smem_off + (size_t)(2 * NT + 3 * D) * kSyncThreads * sizeof(double)) + threadIdx.x
+                               : a.vseq + chain;
+  const int rTC = NT, rBP = 2 * NT, rBC = 2 * NT + D;           // first rows of tcand, bprop, bcoin
+  if (in_smem) {
+    for (int t = 0; t < NT; ++t) wk[(unsigned long long)t * ws] = a.tval[(unsigned long long)t * C + chain];
+    for (int c = 0; c < D; ++c) sp[(unsigned long long)c * ws] = a.state[(unsigned long long)c * C + chain];
+  }
+  const bool wr = valid || in_smem;                             // may this thread write its working set? (a shadow's shared column is its own)
 
   RandomStream g;
   g.init(a.rng_n[chain]);
   unsigned long long perm = a.perm[chain];
   double curr = a.curr_lp[chain];
-  const int P = m.n_params, D = m.D;
   unsigned char order[kMaxDim0];
 
   long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
@@ -936,9 +972,9 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
           int e = sa.monitor[j];
           double v;
           if (e < D) {
-            v = st[(unsigned long long)e * C];
+            v = sp[(unsigned long long)e * ws];
           } else {
-            if (!have_der) { EvalState es{st, C, -1, 0.0}; run_ctx(ctx, es, derived_pc(m, es), der, false); have_der = true; }
+            if (!have_der) { EvalState es{sp, ws, -1, 0.0}; run_ctx(ctx, es, derived_pc(m, es), der, false); have_der = true; }
             v = der[e - D];
           }
           sa.out[((unsigned long long)row * sa.n_monitor + j) * C + chain] = v;
@@ -947,6 +983,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
       if (rec_now) ++row;
     }
     // ---- (a) this sweep's random numbers, in the reference's order
+    if (m.stat_barriers) __syncthreads();
     for (int i = P - 1; i > 0; --i) {                           // shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
       int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
       unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
@@ -967,47 +1004,51 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
       for (int r = 0; r < pa.n_comp; ++r, ++pos) {
         int c = pa.comp_offset;
         if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
-        const unsigned long long ci = (unsigned long long)c * C + chain;
-        const double cur = a.state[ci];
-        double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[ci]);          // generate_proposal (mcmc.js:519, 577-579 / 596-598)
+        const double cur = sp[(unsigned long long)c * ws];
+        double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[(unsigned long long)c * C + chain]);   // generate_proposal (mcmc.js:519, 577-579 / 596-598)
         if (pa.type == AMWG_INT) prop = js_round(prop);
         const bool inb = !(prop < pa.lower || prop > pa.upper);              // bounds check (:520): no uniform when it fails
         const double coin = inb ? g.next(a.seed, gchain) : -1.0;
-        if (valid) {
-          a.bprop[ci] = inb ? prop : cur;
-          a.bcoin[ci] = coin;
-          a.vseq[(unsigned long long)pos * C + chain] = (unsigned short)c;
+        if (wr) {
+          wk[(unsigned long long)(rBP + c) * ws] = inb ? prop : cur;
+          wk[(unsigned long long)(rBC + c) * ws] = coin;
+          vq[(unsigned long long)pos * ws] = (unsigned short)c;
         }
       }
     }
     // ---- (b) one pass over the data: every plate statistic at the proposals -> candidate slots
+    if (m.stat_barriers) __syncthreads();
     {
-      EvalState es{st, C, -1, 0.0};
-      es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
-      es.bprop = a.bprop + chain; es.blk_lo = 0; es.blk_hi = D;
-      if (!valid) es.tval = nullptr;                            // shadow threads compute along (barriers) and store nothing
+      EvalState es{sp, ws, -1, 0.0};
+      es.tval = wr ? wk : nullptr;                              // a shadow of a global column computes along (barriers) and stores nothing
+      es.tcand = wk + (unsigned long long)rTC * ws; es.tstride = ws;
+      es.bprop = wk + (unsigned long long)rBP * ws; es.blk_lo = 0; es.blk_hi = D;
       eval_logpost<true>(ctx, es, m.stat_prog);
     }
     // ---- (c) the steps, in visiting order: O(1) each
-    if (valid) {
-      for (int i = 0; i < D; ++i) {
-        const int c = (int)a.vseq[(unsigned long long)i * C + chain];
-        const unsigned long long ci = (unsigned long long)c * C + chain;
-        const double coin = a.bcoin[ci];
-        if (coin < 0.0) continue;                               // out of bounds: rejected without evaluation (mcmc.js:520-522)
-        const double prop = a.bprop[ci];
-        EvalState es{st, C, c, prop};
-        es.tval = a.tval + chain; es.tcand = a.tcand + chain; es.tstride = C;
-        const double lp_new = eval_logpost<true>(ctx, es, ctx.comp_prog[c]);
-        const double accept_prob = js_exp(lp_new - curr);       // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
-        if (accept_prob > coin) {
-          curr = lp_new;
-          a.state[ci] = prop;
-          if (m.adapting[c]) a.acc[ci] += 1;
-          for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
-            const unsigned long long ti = (unsigned long long)ctx.touch_terms[k] * C + chain;
-            a.tval[ti] = a.tcand[ti];
-          }
+    int c_next = (int)vq[0];
+    double coin_next = wk[(unsigned long long)(rBC + c_next) * ws], prop_next = wk[(unsigned long long)(rBP + c_next) * ws];
+    for (int i = 0; i < D; ++i) {
+      if (m.stat_barriers && D <= 8) __syncthreads();           // few steps: keep the CTA's warps in the same code (instruction cache)
+      const int c = c_next;
+      const double coin = coin_next, prop = prop_next;
+      if (i + 1 < D) {                                          // the next step's operands are on their way while this one is evaluated
+        c_next = (int)vq[(unsigned long long)(i + 1) * ws];
+        coin_next = wk[(unsigned long long)(rBC + c_next) * ws]; prop_next = wk[(unsigned long long)(rBP + c_next) * ws];
+      }
+      if (!wr || coin < 0.0) continue;                          // out of bounds: rejected without evaluation (mcmc.js:520-522)
+      const bool adapting = m.adapting[c] != 0;
+      EvalState es{sp, ws, c, prop};
+      es.tval = wk; es.tcand = wk + (unsigned long long)rTC * ws; es.tstride = ws;
+      const double lp_new = eval_logpost<true>(ctx, es, ctx.comp_prog[c]);
+      const double accept_prob = js_exp(lp_new - curr);         // Metropolis accept (mcmc.js:527-534): strict >, NaN rejects
+      if (accept_prob > coin) {
+        curr = lp_new;
+        sp[(unsigned long long)c * ws] = prop;
+        if (adapting && valid) atomicAdd(&a.acc[(unsigned long long)c * C + chain], 1);      // result unused: a fire-and-forget RED
+        for (int k = ctx.touch_off[c]; k < ctx.touch_off[c + 1]; ++k) {
+          const unsigned long long t = (unsigned long long)ctx.touch_terms[k];
+          wk[t * ws] = wk[(t + rTC) * ws];
         }
       }
     }
@@ -1016,6 +1057,10 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
     a.rng_n[chain] = g.n;
     a.perm[chain] = perm;
     a.curr_lp[chain] = curr;
+    if (in_smem) {
+      for (int t = 0; t < NT; ++t) a.tval[(unsigned long long)t * C + chain] = wk[(unsigned long long)t * ws];
+      for (int c = 0; c < D; ++c) a.state[(unsigned long long)c * C + chain] = sp[(unsigned long long)c * ws];
+    }
   }
 }
 
@@ -1272,6 +1317,8 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     if (const char* e = getenv("AMWG_STAT_SWEEP")) off = off || atoi(e) == 0;
     if (off) { m.stat_prog = -1; m.n_terms = 0; m.n_block_params = 0; }
   }
+  m.stat_barriers = 1;
+  if (const char* e = getenv("AMWG_STAT_BARRIERS")) m.stat_barriers = atoi(e) != 0;
   m.image_bytes = (unsigned)image.size();
   unsigned char* d_image = nullptr;
   if (dev_upload(s, image.data(), image.size(), &d_image)) return bail(-1);
@@ -1313,6 +1360,15 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     if (smem_used + m.col_bytes[k] <= resident_budget) { m.col_smem_off[k] = (int)smem_used; smem_used += m.col_bytes[k]; }
     else m.col_smem_off[k] = -1;       // too large for shared memory: served from L2 (streamed tiles: DESIGN.md "next")
   }
+  // working set of a statistics sweep in shared memory, when 7 CTAs per SM still fit (the register cap's occupancy)
+  m.scratch_smem_off = -1;
+  if (m.stat_prog >= 0) {
+    const size_t per_thread = sizeof(double) * (size_t)(2 * m.n_terms + 3 * md->n_comp) + sizeof(unsigned short) * (size_t)md->n_comp;
+    const size_t need = pad16(per_thread * kSyncThreads);
+    bool use = pad16(smem_used) + need <= (227u * 1024u) / 7u - 1024u;
+    if (const char* e = getenv("AMWG_STAT_SMEM")) use = use && atoi(e) != 0;
+    if (use) { m.scratch_smem_off = (int)pad16(smem_used); smem_used = (unsigned)(pad16(smem_used) + need); }
+  }
   s->smem_bytes = smem_used;
   // chains per thread: 1. The W = 2 / 4 variants (amwg_wide.cuh) execute 22 % fewer instructions per chain-step but need 168
   // registers (12 warps/SM) and measure 0.77x / 0.61x on config 2 (profiles/r01w); AMWG_CHAINS_PER_THREAD selects them for experiments.
@@ -1339,10 +1395,12 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     return bail(-1);
   a.tval = a.tcand = a.bprop = a.bcoin = nullptr;
   a.vseq = nullptr;
-  if ((m.n_block_params > 0 || m.stat_prog >= 0) && (dev_alloc(s, DC, &a.bprop) || dev_alloc(s, DC, &a.bcoin))) return bail(-1);
-  if (m.stat_prog >= 0 && dev_alloc(s, DC, &a.vseq)) return bail(-1);
   if (m.n_terms > 0) {
-    if (dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tval) || dev_alloc(s, (size_t)m.n_terms * (size_t)n_chains, &a.tcand)) return bail(-1);
+    // one allocation, rows [tval n_terms | tcand n_terms | bprop D | bcoin D] x C: amwg_stat_sweep_kernel addresses them as one block
+    const size_t TC = (size_t)m.n_terms * (size_t)n_chains;
+    if (dev_alloc(s, 2 * TC + 2 * DC, &a.tval)) return bail(-1);
+    a.tcand = a.tval + TC; a.bprop = a.tcand + TC; a.bcoin = a.bprop + DC;
+    if (m.stat_prog >= 0 && dev_alloc(s, DC, &a.vseq)) return bail(-1);
     s->chains_per_thread = 1;            // the experimental wide kernel evaluates the full program only
   }
 

@@ -939,7 +939,12 @@ class Lowering:
         parameter; enough plate points for one data pass per sweep (instead of one per step) to matter."""
         terms = self._terms
         plates = [tr for tr in terms if "plate_kind" in tr]
-        if os.environ.get("AMWG_STAT_LOWERING", "1") == "0":          # A/B runs and the tests of the other evaluation modes
+        mode = os.environ.get("AMWG_STAT_LOWERING", "1")              # 0: never, 2: whenever eligible (A/B runs, tests), 1: when it pays
+        if mode == "0":
+            return False
+        # Measured on B200 (DESIGN.md): with two components the sweep saves one of two data passes but pays for it in bookkeeping
+        # (2.4e9 vs 2.5e9 draws/s on the headline model); from three components on it wins.
+        if mode != "2" and self.n_comp <= 2:
             return False
         if not plates or any(ptype == "binary" for _, _, ptype in self.param_ranges) or not self.param_ranges:
             return False

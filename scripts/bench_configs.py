@@ -112,9 +112,9 @@ def config4():
     s = mcmc.AmwgSampler(P4, hier, {"y": yy.tolist(), "g": g.tolist()}, {"chains": 1 << 16, "seed": 0})
     t_trace = time.perf_counter() - t0
     r, ms = gpu_rate(s, 2, 4, reps=2)
-    emit(config=4, what="GPU, hierarchical Normal N=65536, D=65, 2^16 chains on one GPU (the BASELINE per-GPU share); block step for mu (all 64 "
-         "group means proposed together, ONE evaluation, sequential accepts from the per-chain term cache) + one evaluation for sigma: "
-         "131072 point-terms per sweep instead of 65 x 65536; y (512 KB) streamed through the TMA tile ring", draws_per_s=r,
+    emit(config=4, what="GPU, hierarchical Normal N=65536, D=65, 2^16 chains on one GPU (the BASELINE per-GPU share); pre-evaluated statistics: "
+         "all 65 proposals drawn first, ONE pass over y (512 KB through the TMA tile ring) gives every group's sum of squares at its proposal, "
+         "then 65 O(1) steps from cached terms: 65536 point-terms per sweep instead of 65 x 65536", draws_per_s=r,
          trace_seconds=t_trace, n_plates=len(s._program.plates), program=s.program_summary()[-1])
     del s
     t = orc.time_model("hier_norm", {"y": yy, "g": g}, P4, chains=1, burn=0, sample=3)
