@@ -198,17 +198,29 @@ def run_ours(args):
     clk = clocks.stop() if clocks else None
 
     # ---- e2e: public API, host arrays ---------------------------------------------------------------------------
+    # N > 1: every process receives the draws of its own chains in its own host memory (options.gather = "none": one PCIe link
+    # per GPU, the way a one-process-per-GPU job consumes them); the variant where rank 0 alone ends up with all chains
+    # (gather = "root": NCCL gather first, then ONE host copy) is timed beside it as e2e_gather_root.
     e2e_steps = max(1, min(args.steps, 5 if world == 1 else 3))
-    w1 = sampler.sample(iters)                 # warm-up: two live results = the two pinned buffers the loop alternates between
-    w2 = sampler.sample(iters)
-    del w1, w2
-    barrier()
-    t1 = time.perf_counter()
-    for _ in range(e2e_steps):
-        draws = sampler.sample(iters)
-    barrier()
-    dt_e2e = time.perf_counter() - t1
-    assert draws["mu"].shape == (iters, chains_total if rank == 0 else local)      # gather="root": rank 0 holds every chain
+
+    def e2e_leg(mode, steps):
+        sampler.gather = mode
+        w1 = sampler.sample(iters)             # warm-up: two live results = the two pinned buffers the loop alternates between
+        w2 = sampler.sample(iters)
+        del w1, w2
+        barrier()
+        t = time.perf_counter()
+        for _ in range(steps):
+            draws = sampler.sample(iters)
+        barrier()
+        dt_leg = time.perf_counter() - t
+        want = chains_total if (mode == "root" and rank == 0) else local
+        assert draws["mu"].shape == (iters, want)
+        return dt_leg
+
+    dt_e2e = e2e_leg("none", e2e_steps)
+    root_steps = 2
+    dt_root = e2e_leg("root", root_steps) if world > 1 else 0.0
 
     # ---- e2e with the summary formed on the device: same sweeps, only mean/sd/quantiles/R-hat leave the GPUs
     summ = sampler.sample_summary(iters)       # warm-up
@@ -219,10 +231,10 @@ def run_ours(args):
     barrier()
     dt_sum = time.perf_counter() - t2
 
-    times = torch.tensor([dt, dt_e2e, kernel_ms, dt_sum], dtype=torch.float64, device=f"cuda:{local_rank}")
+    times = torch.tensor([dt, dt_e2e, kernel_ms, dt_sum, dt_root], dtype=torch.float64, device=f"cuda:{local_rank}")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    dt, dt_e2e, kernel_ms, dt_sum = [float(v) for v in times.tolist()]
+    dt, dt_e2e, kernel_ms, dt_sum, dt_root = [float(v) for v in times.tolist()]
 
     if rank == 0:
         draws_per_step = chains_total * iters
@@ -254,7 +266,9 @@ def run_ours(args):
             "e2e": {"value": e2e, "unit": "draws/s", "h2d_bytes_per_step": int(mon.nbytes),
                     "d2h_bytes_per_step": int(iters * 2 * chains_total * 8), "steps": e2e_steps,
                     "note": "mcmc.AmwgSampler.sample(): pinned host buffer, D2H overlapped with the sweeps"
-                            + ("; NCCL gather of the shards to rank 0 first (gather=\"root\": one host copy of all draws)" if world > 1 else "")},
+                            + ("; every rank copies the draws of its own chains to its own host memory (gather=\"none\")" if world > 1 else "")},
+            "e2e_gather_root": ({"value": draws_per_step * root_steps / dt_root, "unit": "draws/s", "steps": root_steps,
+                                 "note": "gather=\"root\": NCCL gather of the shards to rank 0, one host copy of all draws"} if world > 1 else None),
             "e2e_summary": {"value": draws_per_step * e2e_steps / dt_sum, "unit": "draws/s", "steps": e2e_steps,
                             "d2h_bytes_per_step": 2 * 4 * 8 + 8 * 2 * 10 * 256 * 8,
                             "mu": {"mean": summ["mu"]["mean"], "sd": summ["mu"]["sd"], "rhat": summ["mu"]["rhat"],
