@@ -59,10 +59,26 @@ __global__ void __launch_bounds__(256) amwg_chain_moments_kernel(const double* _
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
     const double* p = x + (size_t)e * C + c;
     double s = 0.0;
-    for (long long r = 0; r < rows; ++r) s += p[r * stride];
+    long long r = 0;
+    for (; r + 8 <= rows; r += 8) {                          // eight loads in flight per thread, the sum stays sequential
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(r + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; r < rows; ++r) s += p[r * stride];
     const double m = s / (double)rows;
     double m2 = 0.0;
-    for (long long r = 0; r < rows; ++r) { double d = p[r * stride] - m; m2 = fma(d, d, m2); }
+    r = 0;
+    for (; r + 8 <= rows; r += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(r + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { double d = v[u] - m; m2 = fma(d, d, m2); }
+    }
+    for (; r < rows; ++r) { double d = p[r * stride] - m; m2 = fma(d, d, m2); }
     acc = merge(acc, Moments{1.0, m, 0.0, m2});
   }
   const Moments tot = cta_merge<256>(sh, acc);
@@ -91,6 +107,8 @@ __global__ void __launch_bounds__(256) amwg_digit_hist_kernel(const double* __re
   for (int i = threadIdx.x; i < n_prefix * 256; i += blockDim.x) hist[i] = 0u;
   if (threadIdx.x < n_prefix) pre[threadIdx.x] = prefix[(size_t)e * n_prefix + threadIdx.x];
   __syncthreads();
+  unsigned long long pre_lo = pre[0], pre_hi = pre[0];        // most values lie outside [lowest, highest] prefix in the late passes
+  for (int q = 1; q < n_prefix; ++q) { pre_lo = pre[q] < pre_lo ? pre[q] : pre_lo; pre_hi = pre[q] > pre_hi ? pre[q] : pre_hi; }
   const int shift = 56 - 8 * pass;
   const size_t stride = (size_t)entries * C;
   for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < C; c += (long long)gridDim.x * blockDim.x) {
@@ -99,19 +117,28 @@ __global__ void __launch_bounds__(256) amwg_digit_hist_kernel(const double* __re
     // run in a register and touch the shared histogram once per run instead of once per value
     int last = -1;
     unsigned int run = 0;
-    for (long long r = 0; r < rows; ++r) {
-      const unsigned long long k = ordered_key(p[r * stride]);
+    auto count = [&](double x) {
+      const unsigned long long k = ordered_key(x);
       int idx = (int)((k >> shift) & 255ull);
       if (pass) {
         const unsigned long long hi = k >> (shift + 8);
-        int q = 0;
-        while (q < n_prefix && pre[q] != hi) ++q;           // prefixes are distinct: at most one matches
+        int q = n_prefix;
+        if (hi >= pre_lo && hi <= pre_hi) { q = 0; while (q < n_prefix && pre[q] != hi) ++q; }   // the first match counts (padding repeats a prefix)
         idx = (q < n_prefix) ? q * 256 + idx : -1;
       }
-      if (idx == last) { ++run; continue; }
+      if (idx == last) { ++run; return; }
       if (last >= 0) atomicAdd(&hist[last], run);
       last = idx; run = 1;
+    };
+    long long r = 0;
+    for (; r + 8 <= rows; r += 8) {                          // eight loads in flight per thread
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = p[(r + u) * stride];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) count(v[u]);
     }
+    for (; r < rows; ++r) count(p[r * stride]);
     if (last >= 0) atomicAdd(&hist[last], run);
   }
   __syncthreads();

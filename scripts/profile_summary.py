@@ -16,11 +16,13 @@ def T(f, n=3):
     f(); torch.cuda.synchronize(); t = time.perf_counter()
     for _ in range(n): r = f()
     torch.cuda.synchronize(); return (time.perf_counter() - t) / n * 1e3, r
-print("moments ms", T(lambda: red.moments(block))[0])
+gb = rows * entries * chains * 8 / 1e9
+ms = T(lambda: red.moments(block))[0]
+print("moments: %.3f ms incl. launch/alloc/D2H; reads the block twice: %.0f GB/s" % (ms, 2 * gb / ms * 1e3))
 ranks, plan = quantile_targets(rows * chains, (0.025, 0.25, 0.5, 0.75, 0.975))
 sel = RadixSelect(entries, ranks)
 for p in range(8):
     table, which = sel.prefixes()
     ms, counts = T(lambda: red.digit_counts(block, p, table))
     t = time.perf_counter(); sel.advance(counts.cpu().numpy(), which); host = (time.perf_counter() - t) * 1e3
-    print("pass", p, "n_prefix", table.shape[1], "kernel+launch ms %.3f" % ms, "host advance ms %.3f" % host)
+    print("pass", p, "n_prefix", table.shape[1], "kernel+launch ms %.3f (%.0f GB/s)" % (ms, gb / ms * 1e3), "host advance ms %.3f" % host)
