@@ -16,8 +16,7 @@ LIB_PATH = os.path.join(_HERE, "libamwg_b200.so")
 _OPS = """END CONST COMP DATA DATA_I COMP_I ADD SUB MUL DIV NEG LOG EXP SQRT ABS POW LT LE GT GE EQ NE AND OR NOT SELECT
 LGAMMA LFACTORIAL LCHOOSE LBETA LD_NORM LD_UNIF LD_BETA LD_BERN LD_POIS LD_CAUCHY LD_LAPLACE LD_GAMMA LD_INVGAMMA
 LD_LNORM LD_PARETO LD_T LD_WEIBULL LD_LOGIS LD_EXP LD_BINOM LD_NBINOM LD_HYPER ACC PLATE STORE LOOP_BEGIN LOOP_END
-NORM_K UNIF_K BETA_K ACC_RANGE PLATE_SS NORM_SS CACHED CAND
-NORM_K_F UNIF_K_F BETA_K_F PLATE_NORM_F""".split()
+NORM_K UNIF_K BETA_K ACC_RANGE PLATE_SS NORM_SS CACHED CAND""".split()
 OP = {name: i for i, name in enumerate(_OPS)}
 OP_COUNT = len(_OPS)
 PLATE_GENERIC, PLATE_NORM_IID, PLATE_BERN_IID, PLATE_NORM_GROUPED, PLATE_POIS_LOGLIN = range(5)

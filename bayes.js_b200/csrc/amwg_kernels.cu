@@ -506,7 +506,7 @@ __device__ __noinline__ double run_program_t(unsigned code_sa, unsigned consts_s
     const int a = (int)(w >> 18);
     // operands, last one first (the order inline words are laid out and stack operands are popped)
     double x = 0.0, y = 0.0, z = 0.0, t = 0.0;
-    if (op != AMWG_OP_PLATE && (w & 0xff00u) != 0xff00u) {   // plates fetch their own operands; all-NONE: nothing to fetch
+    if (op != AMWG_OP_PLATE) {                          // plates fetch their own operands
       const int mD = (w >> 14) & 3, mC = (w >> 12) & 3, mB = (w >> 10) & 3, mA = (w >> 8) & 3;
       if (mD != AMWG_MODE_NONE) AMWG_OPND(t, mD);
       if (mC != AMWG_MODE_NONE) AMWG_OPND(z, mC);
@@ -557,33 +557,6 @@ __device__ __noinline__ double run_program_t(unsigned code_sa, unsigned consts_s
       case AMWG_OP_NORM_SS: r = norm_factorised(ctx, (double)ctx.plates[a].n, x, y); break;
       case AMWG_OP_CACHED: r = es.cached(a); break;
       case AMWG_OP_CAND: r = es.cand(a); break;
-      case AMWG_OP_NORM_K_F: {               // fixed-operand forms: the words follow in source order
-        const int c = AMWG_NEXT(); const int i1 = AMWG_NEXT(), i2 = AMWG_NEXT(), i3 = AMWG_NEXT();
-        const double d = es.comp(c) - lds_f64(consts_sa + 8u * (unsigned)i1);
-        r = lds_f64(consts_sa + 8u * (unsigned)i2) - (d * d) / lds_f64(consts_sa + 8u * (unsigned)i3);
-        break;
-      }
-      case AMWG_OP_UNIF_K_F: {
-        const int c = AMWG_NEXT(); const int i1 = AMWG_NEXT(), i2 = AMWG_NEXT(), i3 = AMWG_NEXT();
-        const double v = es.comp(c);
-        r = (v < lds_f64(consts_sa + 8u * (unsigned)i1) || v > lds_f64(consts_sa + 8u * (unsigned)i2)) ? -CUDART_INF : lds_f64(consts_sa + 8u * (unsigned)i3);
-        break;
-      }
-      case AMWG_OP_BETA_K_F: {
-        const int c = AMWG_NEXT(); const int i1 = AMWG_NEXT(), i2 = AMWG_NEXT(), i3 = AMWG_NEXT();
-        const double v = es.comp(c);
-        r = (v > 1 || v < 0) ? -CUDART_INF
-                             : (lds_f64(consts_sa + 8u * (unsigned)i1) * js_log(v) + lds_f64(consts_sa + 8u * (unsigned)i2) * js_log(1 - v)) - lds_f64(consts_sa + 8u * (unsigned)i3);
-        break;
-      }
-      case AMWG_OP_PLATE_NORM_F: {
-        has_r = false;
-        const int cm = AMWG_NEXT(), cs = AMWG_NEXT();
-        const double v = plate_norm_iid(ctx, a, es.comp(cm), es.comp(cs));
-        lp = lp + v;
-        if (store) { const int t = AMWG_NEXT(); es.store(t, v); }
-        break;
-      }
       case AMWG_OP_ACC: { double v; AMWG_POP(v); lp = lp + v; has_r = false; break; }
       case AMWG_OP_ACC_RANGE: {              // terms that do not read the moved component: their cached values, one by one, in order
         const int cnt = AMWG_NEXT();

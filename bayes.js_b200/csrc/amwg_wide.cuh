@@ -196,30 +196,6 @@ __device__ __noinline__ void run_logpost_w(unsigned code_sa, unsigned consts_sa,
       case AMWG_OP_NORM_K: WEACH(z[k] - ((x[k] - y[k]) * (x[k] - y[k])) / t[k])
       case AMWG_OP_UNIF_K: WEACH((x[k] < y[k] || x[k] > z[k]) ? -CUDART_INF : t[k])
       case AMWG_OP_BETA_K: WEACH((x[k] > 1 || x[k] < 0) ? -CUDART_INF : (y[k] * js_log(x[k]) + z[k] * js_log(1 - x[k])) - t[k])
-      case AMWG_OP_NORM_K_F: case AMWG_OP_UNIF_K_F: case AMWG_OP_BETA_K_F: {     // fixed-operand forms (amwg.h): words in source order
-        const int c = WNEXT(); const int i1 = WNEXT(), i2 = WNEXT(), i3 = WNEXT();
-        const double k1 = lds_f64(consts_sa + 8u * (unsigned)i1), k2 = lds_f64(consts_sa + 8u * (unsigned)i2), k3 = lds_f64(consts_sa + 8u * (unsigned)i3);
-#pragma unroll
-        for (int k = 0; k < W; ++k) {
-          const double v = es.comp(k, c);
-          if (op == AMWG_OP_NORM_K_F) { const double d = v - k1; r[k] = k2 - (d * d) / k3; }
-          else if (op == AMWG_OP_UNIF_K_F) r[k] = (v < k1 || v > k2) ? -CUDART_INF : k3;
-          else r[k] = (v > 1 || v < 0) ? -CUDART_INF : (k1 * js_log(v) + k2 * js_log(1 - v)) - k3;
-        }
-        break;
-      }
-      case AMWG_OP_PLATE_NORM_F: {
-        has_r = false;
-        const int cm = WNEXT(), cs = WNEXT();
-        double mean[W], sd[W], v[W];
-#pragma unroll
-        for (int k = 0; k < W; ++k) { mean[k] = es.comp(k, cm); sd[k] = es.comp(k, cs); }
-        plate_norm_iid_w<W>(ctx, a, mean, sd, v);
-#pragma unroll
-        for (int k = 0; k < W; ++k) lp[k] = lp[k] + v[k];
-        if (store) (void)WNEXT();
-        break;
-      }
       case AMWG_OP_ACC: {
         double v[W]; WPOP(v);
 #pragma unroll

@@ -643,11 +643,6 @@ class Lowering:
         else:
             if n.op not in _ARITY:
                 raise JsThrow(f"cannot lower operation {n.op}")
-            if n.op in ("NORM_K", "UNIF_K", "BETA_K"):
-                il = [self._inline(a) for a in n.args]
-                if all(x is not None for x in il) and [m for m, _ in il] == [MODE_COMP, MODE_CONST, MODE_CONST, MODE_CONST]:
-                    p.emit(n.op + "_F", 0, *[w for _, w in il], acc=acc, store=store)     # fixed-operand form: nothing to decode
-                    return
             modes, words = self._operands(n.args)
             p.emit(n.op, 0, *words, modes=modes, acc=acc, store=store)
 
@@ -745,10 +740,7 @@ class Lowering:
             modes, words = self._operands(prepared)
             value_plate = pl["kind"] != PLATE_BERN_IID              # the Bernoulli plate adds term by term into lp: not a separable value
             tid = len(self._terms) if (self._record_terms and value_plate) else None
-            if pl["kind"] == PLATE_NORM_IID and modes == [MODE_COMP, MODE_COMP]:
-                p.emit("PLATE_NORM_F", q, *reversed(words), store=tid)                    # words back in source order: mean, sd
-            else:
-                p.emit("PLATE", q, *words, modes=modes, store=tid)
+            p.emit("PLATE", q, *words, modes=modes, store=tid)
             if self._record_terms:
                 deps = set()
                 for o in prepared:

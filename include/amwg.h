@@ -129,12 +129,6 @@ enum {
   AMWG_OP_NORM_SS,      /* (S, sd): f(S, sd) of plate `a` (same operations as AMWG_PLATE_NORM_IID, given its S)                */
   AMWG_OP_CACHED,       /* push cache[a]      : the committed value of slot a (a statistic of the chain's current state)       */
   AMWG_OP_CAND,         /* push candidate[a]  : the value the last stat_prog evaluation computed for slot a (at the proposals)   */
-  /* Fixed-operand forms of the hottest instructions: no operand modes to decode (all four mode fields are NONE); the operand words
-   * follow in SOURCE order. Same operations, same bits as the general form. */
-  AMWG_OP_NORM_K_F,     /* NORM_K(state[w1], consts[w2], consts[w3], consts[w4])                                                */
-  AMWG_OP_UNIF_K_F,     /* UNIF_K(state[w1], consts[w2], consts[w3], consts[w4])                                                */
-  AMWG_OP_BETA_K_F,     /* BETA_K(state[w1], consts[w2], consts[w3], consts[w4])                                                */
-  AMWG_OP_PLATE_NORM_F, /* PLATE on the NORM_IID plate `a` with mean = state[w1], sd = state[w2] (then the term id when STORE)   */
   AMWG_OP__COUNT
 };
 

@@ -92,25 +92,6 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0,
                 r = -math.inf if (x < y or x > z) else t
             else:
                 r = -math.inf if (x > 1 or x < 0) else (y * O.orc_log(x) + z * O.orc_log(1 - x)) - t
-        elif op in ("NORM_K_F", "UNIF_K_F", "BETA_K_F"):
-            x = comp(nxt()); y = consts[nxt()]; z = consts[nxt()]; t = consts[nxt()]
-            if op == "NORM_K_F":
-                d = x - y; r = z - div(d * d, t)
-            elif op == "UNIF_K_F":
-                r = -math.inf if (x < y or x > z) else t
-            else:
-                r = -math.inf if (x > 1 or x < 0) else (y * O.orc_log(x) + z * O.orc_log(1 - x)) - t
-        elif op == "PLATE_NORM_F":
-            mean = comp(nxt()); sd = comp(nxt())
-            pl = plates[a]
-            x = np.asarray(cols[pl["col"][0]][pl["iparam"][2]:pl["iparam"][2] + pl["n"]], dtype=np.float64)
-            S = float(np.sum((x - mean) ** 2))
-            plate_v = pl["n"] * (-0.5 * O.orc_log(2 * JS_PI) - O.orc_log(sd)) - S / (2 * sd * sd)
-            lp = lp + plate_v
-            if store:
-                t_id = nxt()
-                if cache is not None:
-                    (cand if cand is not None else cache)[t_id] = plate_v
         elif op.startswith("LD_"):
             n = {"LD_BERN": 2, "LD_POIS": 2, "LD_EXP": 2, "LD_T": 4, "LD_HYPER": 4}.get(op, 3)
             args = [opnd(m) for m in (mA, mB, mC, mD)[:n][::-1]][::-1]
