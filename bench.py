@@ -226,8 +226,11 @@ def run_ours(args):
     summ = sampler.sample_summary(iters)       # warm-up
     barrier()
     t2 = time.perf_counter()
+    sum_ms = []
     for _ in range(e2e_steps):
+        t3 = time.perf_counter()
         summ = sampler.sample_summary(iters)
+        sum_ms.append(round(1e3 * (time.perf_counter() - t3), 2))
     barrier()
     dt_sum = time.perf_counter() - t2
 
@@ -270,7 +273,8 @@ def run_ours(args):
             "e2e_gather_root": ({"value": draws_per_step * root_steps / dt_root, "unit": "draws/s", "steps": root_steps,
                                  "note": "gather=\"root\": NCCL gather of the shards to rank 0, one host copy of all draws"} if world > 1 else None),
             "e2e_summary": {"value": draws_per_step * e2e_steps / dt_sum, "unit": "draws/s", "steps": e2e_steps,
-                            "d2h_bytes_per_step": 2 * 4 * 8 + 8 * 2 * 10 * 256 * 8,
+                            "d2h_bytes_per_step": 2 * 4 * 8 + 8 * 2 * 10 * 256 * 8, "ms_per_call_rank0": sum_ms,
+                            "median_call_value": draws_per_step / (1e-3 * sorted(sum_ms)[len(sum_ms) // 2]),
                             "mu": {"mean": summ["mu"]["mean"], "sd": summ["mu"]["sd"], "rhat": summ["mu"]["rhat"],
                                    "q2.5_50_97.5": [float(summ["mu"]["quantiles"][i]) for i in (0, 2, 4)]},
                             "note": "mcmc.AmwgSampler.sample_summary(): the draws stay in HBM; pooled mean/sd, exact quantiles (8-pass radix "
