@@ -1,5 +1,6 @@
 """Host logic that mirrors mcmc.js, against the reference's own golden fixtures (tests/test_data.js) -- no GPU."""
 import copy
+import os
 import ctypes
 import re
 
@@ -120,3 +121,24 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/`` holds", "").replace("``oracle/``", ""), f
+
+
+def test_bench_reference_arm_runs_on_cpu_and_the_product_arm_refuses_without_a_gpu():
+    """bench.py --impl reference times the CPU restatement (the one place outside tests/ and smoke() that may execute oracle/);
+    the product arm has no CPU fallback: without a CUDA device it exits with an error instead of printing a number."""
+    import json
+    import subprocess
+    import sys
+    import torch
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "draws/s" and line["value"] > 0 and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0 and line["gpu_launches"] == 0
+    if not torch.cuda.is_available():
+        r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "1", "--warmup", "0"],
+                           capture_output=True, text=True, timeout=600, cwd=root)
+        assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
