@@ -105,12 +105,35 @@ var spike_bern = function(state, data) {
   }
   return log_post;
 };
+var hier_norm_post = function(state, data) {
+  var log_post = 0;
+  for(var j = 0; j < state.mu.length; j++) { log_post += ld.norm(state.mu[j], 0, 100); }
+  log_post += ld.unif(state.sigma, 0, 100);
+  for(var i = 0; i < data.y.length; i++) { log_post += ld.norm(data.y[i], state.mu[data.g[i]], state.sigma); }
+  return log_post;
+};
+var pois_reg_post = function(state, data) {
+  var log_post = 0;
+  for(var k = 0; k < state.beta.length; k++) { log_post += ld.norm(state.beta[k], 0, 10); }
+  for(var i = 0; i < data.y.length; i++) {
+    var eta = 0;
+    for(var k = 0; k < state.beta.length; k++) { eta += data.X[i][k] * state.beta[k]; }
+    log_post += ld.pois(data.y[i], Math.exp(eta));
+  }
+  return log_post;
+};
 """
 
 PRESIDENTS = [183, 192, 182, 183, 177, 185, 188, 188, 182, 185]
 Y8 = [1, 0, 1, 1, 0, 1, 1, 1]
 Y40 = [int(v) for v in (np.random.default_rng(40).random(40) < 0.7)]
 NB12 = [int(v) for v in np.random.default_rng(7).negative_binomial(21, 0.5, 12)]
+# BASELINE configs 4 and 5 in miniature (SURVEY 8(d).4-5): hierarchical Normal (3 groups x 4) and Poisson regression (N = 12, K = 2)
+_rg = np.random.default_rng(45)
+HIER_G = [j for j in range(3) for _ in range(4)]
+HIER_Y = [float(np.round(v, 3)) for v in (np.array([95.0, 100.0, 108.0])[HIER_G] + _rg.normal(0, 5, 12))]
+POIS_X = [[1.0, float(np.round(v, 3))] for v in _rg.normal(0, 0.5, 12)]
+POIS_Y = [int(v) for v in _rg.poisson(np.exp(np.array(POIS_X) @ np.array([0.8, -0.6])))]
 
 # (name, log_post JS expression, params (Python), data (Python), options (Python), script of calls)
 SAMPLER_CASES = [
@@ -139,6 +162,10 @@ SAMPLER_CASES = [
     ("options_or_quirk", "readme_norm_post", {"mu": {"type": "real"}, "sigma": {"type": "real", "lower": 0}}, PRESIDENTS,
      {"is_adapting": True, "prop_log_scale": 2, "batch_size": 7, "params": {"mu": {"is_adapting": False, "prop_log_scale": 0, "batch_size": 0}}},
      [("burn", 30), ("sample", 20)]),
+    ("config4_shape_hierarchical_normal", "hier_norm_post", {"mu": {"type": "real", "dim": [3]}, "sigma": {"type": "real", "lower": 0}},
+     {"y": HIER_Y, "g": HIER_G}, None, [("burn", 120), ("sample", 80)]),
+    ("config5_shape_poisson_regression", "pois_reg_post", {"beta": {"type": "real", "dim": [2]}}, {"y": POIS_Y, "X": POIS_X}, None,
+     [("burn", 120), ("sample", 80)]),
 ]
 
 

@@ -56,6 +56,8 @@ def resolve_case(case, pkg):
         "multi_bern_dens": ("multi_bern_dens", models.multi_bern_dens(mcmc)),
         "complex_model_post": ("complex", models.complex_model_post(ld, mcmc)),
         "hierarchical_binomial_post": ("hier_binom", models.hierarchical_binomial_post(ld, mcmc)),
+        "hier_norm_post": ("hier_norm", models.hier_norm_post(ld)),
+        "pois_reg_post": ("pois_reg", models.pois_reg_post(ld, mcmc)),
     }
     c_model, py_model = table[lp]
     params = PARAMS_BY_NAME[case["params"]] if isinstance(case["params"], str) else case["params"]

@@ -156,3 +156,29 @@ def complex_model_post_literal(ld):
                 log_post += ld.nbinom(x[i], n1, p1)
         return log_post
     return f
+
+
+def hier_norm_post(ld):
+    def f(state, d):                                # BASELINE config 4, any number of groups
+        lp = 0
+        for j in range(len(state.mu)):
+            lp += ld.norm(state.mu[j], 0, 100)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]], state.sigma)
+        return lp
+    return f
+
+
+def pois_reg_post(ld, mcmc):
+    def f(state, d):                                # BASELINE config 5, any number of coefficients
+        lp = 0
+        for k in range(len(state.beta)):
+            lp += ld.norm(state.beta[k], 0, 10)
+        for i in range(len(d.y)):
+            eta = 0
+            for k in range(len(state.beta)):
+                eta += d.X[i][k] * state.beta[k]
+            lp += ld.pois(d.y[i], mcmc.Math.exp(eta))
+        return lp
+    return f
