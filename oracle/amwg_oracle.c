@@ -10,7 +10,7 @@
  * Pinning status (see DESIGN.md "Oracle"):
  *   - pinned DRAW FOR DRAW against the UNMODIFIED /root/reference/mcmc.js + distributions.js + tests/test_data.js, executed
  *     by oracle/minijs (an ES5 interpreter written for this purpose, because no JS engine exists in the image) with
- *     Math.random replaced by the Philox stream below: 28 sampler scenarios covering every stepper kind, options, thin,
+ *     Math.random replaced by the Philox stream below: 32 sampler scenarios covering every stepper kind, options, thin,
  *     monitor and adaptation toggles, plus every ld.* function, complete_params, param_init_fixed and the helpers.
  *     Vectors: tests/golden/reference_js.json; generator: oracle/minijs/make_golden.py; check: tests/test_golden.py;
  *   - pinned against the reference's only deterministic fixtures (complete_params goldens, tests/test_data.js:20-35,50-74)
