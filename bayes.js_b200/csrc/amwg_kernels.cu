@@ -1441,6 +1441,8 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       if (need < (double)L) L = (long long)need;
     }
     if (record && host_out && L > kHostChunkSweeps) L = kHostChunkSweeps;   // finer launches: the D2H of finished rows trails the sweeps closely
+    // ... and the last launches taper off (.., 10, 5, 3, 2), because the copy of the final launch's rows is the one that nothing hides
+    if (record && host_out && n - i0 <= kHostChunkSweeps && L > 2) L = std::min(L, std::max<long long>(2, (n - i0 + 1) / 2));
     SweepArgs sa{L, i0, thin, record, n_monitor, d_monitor, d_out};
     if (n_events >= s->ev_pool.size()) {
       cudaEvent_t e0, e1;
