@@ -108,6 +108,12 @@ def cpu_port_draws_per_sec(orc, seconds_target: float = 12.0):
     return n / t, f"1 chain x {n} draws, N={N_DATA}, single thread"
 
 
+def cpu_baseline_time(model, data, params, chains, burn, sample):
+    """cpu_baseline leg for the other BASELINE configs (scripts/bench_configs.py calls this; like every use of oracle/ outside tests/
+    and smoke(), it lives in bench.py): seconds the CPU restatement takes for `chains` x (burn + sample) draws, one thread."""
+    return graft.load_oracle().time_model(model, data, params, chains=chains, burn=burn, sample=sample)
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (Node is absent), all host cores."""
     rank = int(os.environ.get("RANK", "0"))

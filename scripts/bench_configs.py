@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import __graft_entry__ as graft  # noqa: E402
 
 pkg = graft.load_package()
-orc = graft.load_oracle()
+import bench  # noqa: E402  (the cpu_baseline legs go through bench.py, the one place outside tests/ that executes oracle/)
 mcmc, ld = pkg.mcmc, pkg.ld
 PRESIDENTS = [183, 192, 182, 183, 177, 185, 188, 188, 182, 185]
 
@@ -50,7 +50,7 @@ WANT = set(os.environ.get("CONFIGS", "1,3,4,5").split(","))   # CONFIGS=4 runs o
 
 # config 1: the reference's own CPU-runnable case (README.md:39-42): 1 chain, burn 1000, sample 5000
 def config1():
-    t = orc.time_model("norm_readme", PRESIDENTS, P_NORM, chains=20, burn=1000, sample=5000)
+    t = bench.cpu_baseline_time("norm_readme", PRESIDENTS, P_NORM, 20, 1000, 5000)
     emit(config=1, what="CPU restatement of mcmc.js, presidents data N=10, 1 chain x (1000 burn + 5000 draws), single thread",
          draws_per_s=20 * 6000 / t, note="Node unavailable; README.md:252 reports ~4e4 draws/s at N=1000 on the author's machine")
     s = mcmc.AmwgSampler(P_NORM, norm_post, PRESIDENTS, {"chains": 1 << 20, "seed": 0})
@@ -82,7 +82,7 @@ def config3():
     emit(config=3, what="GPU, Beta-Bernoulli N=256 + binary indicator, 2^20 chains (sequential bit-faithful Bernoulli plate)", draws_per_s=r,
          program=s.program_summary())
     del s
-    t = orc.time_model("spike_bern", {"x": y}, P3, chains=1, burn=0, sample=20000)
+    t = bench.cpu_baseline_time("spike_bern", {"x": y}, P3, 1, 0, 20000)
     emit(config=3, what="CPU restatement, 1 chain x 20000 draws, single thread", draws_per_s=20000 / t)
 
 
@@ -117,7 +117,7 @@ def config4():
          "then 65 O(1) steps from cached terms: 65536 point-terms per sweep instead of 65 x 65536", draws_per_s=r,
          trace_seconds=t_trace, n_plates=len(s._program.plates), program=s.program_summary()[-1])
     del s
-    t = orc.time_model("hier_norm", {"y": yy, "g": g}, P4, chains=1, burn=0, sample=3)
+    t = bench.cpu_baseline_time("hier_norm", {"y": yy, "g": g}, P4, 1, 0, 3)
     emit(config=4, what="CPU restatement, 1 chain x 3 draws, single thread", draws_per_s=3 / t)
 
 
@@ -149,7 +149,7 @@ def config5():
     r, ms = gpu_rate(s, 1, 1, reps=2)
     emit(config=5, what="GPU, Poisson regression N=1e6, K=8, 2^12 chains on one GPU (X 64 MB streamed from L2)", draws_per_s=r, program=s.program_summary()[-1])
     del s
-    t = orc.time_model("pois_reg", {"y": yc, "X": X}, P5, chains=1, burn=0, sample=1)
+    t = bench.cpu_baseline_time("pois_reg", {"y": yc, "X": X}, P5, 1, 0, 1)
     emit(config=5, what="CPU restatement, 1 chain x 1 draw, single thread", draws_per_s=1 / t)
 
 

@@ -121,6 +121,11 @@ def test_product_never_touches_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/`` holds", "").replace("``oracle/``", ""), f
+    # the measurement scripts reach the CPU restatement only through bench.py's cpu_baseline helpers
+    for f in os.listdir(os.path.join(root, "scripts")):
+        if f.endswith(".py"):
+            src = open(os.path.join(root, "scripts", f)).read()
+            assert "load_oracle" not in src and "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
 
 
 def test_bench_reference_arm_runs_on_cpu_and_the_product_arm_refuses_without_a_gpu():
