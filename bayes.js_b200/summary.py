@@ -116,15 +116,14 @@ class RadixSelect:
 
     def advance(self, counts: np.ndarray, which: np.ndarray) -> None:
         """counts [entries, n_prefix, 256] summed over all shards for the prefixes handed out by prefixes()."""
-        for e in range(self.E):
-            for t in range(self.T):
-                cum = np.cumsum(counts[e, which[e, t]].astype(np.int64))
-                d = int(np.searchsorted(cum, self.rem[e, t], side="right"))
-                if d > 255:
-                    raise RuntimeError("radix select: rank beyond the counted values (inconsistent histogram)")
-                if d > 0:
-                    self.rem[e, t] -= cum[d - 1]
-                self.prefix[e, t] = (self.prefix[e, t] << np.uint64(8)) | np.uint64(d)
+        sel = np.take_along_axis(np.asarray(counts, dtype=np.int64), which[:, :, None], axis=1)      # [E, T, 256]: each target's histogram
+        cum = np.cumsum(sel, axis=2)
+        d = (cum <= self.rem[:, :, None]).sum(axis=2)                                             # first byte whose cumulative count exceeds the rank
+        if np.any(d > 255):
+            raise RuntimeError("radix select: rank beyond the counted values (inconsistent histogram)")
+        below = np.take_along_axis(cum, np.maximum(d - 1, 0)[:, :, None], axis=2)[:, :, 0]
+        self.rem = self.rem - np.where(d > 0, below, 0)
+        self.prefix = (self.prefix << np.uint64(8)) | d.astype(np.uint64)
         self.npass += 1
 
     def values(self) -> np.ndarray:
