@@ -527,7 +527,8 @@ class AmwgSampler(Sampler):
         """Not in the reference: the same sweeps and the same kept rows as `sample(n)` (thin / monitor apply), but the
         draws stay in HBM and only their summary comes back: {name: {"mean", "sd", "rhat", "quantiles", "n_draws"}}, pooled over
         all chains and kept rows; multi-dim parameters give arrays of their `dim` ("quantiles": [len(probs), *dim], exact order
-        statistics with numpy.quantile's linear rule). With options.distributed every rank returns the all-GPU summary
+        statistics with numpy.quantile's linear rule; a long grid such as numpy.linspace(0, 1, 41) gives an equal-mass histogram and
+        runs as several radix selects of 16 probabilities each). With options.distributed every rank returns the all-GPU summary
         (two small collectives, summary.py). Advances the chains exactly as sample(n) does."""
         import torch
         from .summary import CudaBlockReducer, summarise_block

@@ -180,8 +180,10 @@ def summarise_block(reducer, block, rows: int, total_chains: int, probs: Sequenc
 
     probs = [float(p) for p in probs]
     q = np.empty((len(probs), entries))
-    if probs:
-        ranks, plan = quantile_targets(rows * total_chains, probs)
+    per_select = MAX_PREFIXES // 2                            # every probability needs at most two order statistics
+    for first in range(0, len(probs), per_select):            # long probability grids (equal-mass histograms): several selects
+        chunk = probs[first:first + per_select]
+        ranks, plan = quantile_targets(rows * total_chains, chunk)
         sel = RadixSelect(entries, ranks)
         for npass in range(8):
             table, which = sel.prefixes()
@@ -192,5 +194,5 @@ def summarise_block(reducer, block, rows: int, total_chains: int, probs: Sequenc
             sel.advance(counts.cpu().numpy(), which)
         vals = sel.values()                                   # [entries, T]
         for i, (lo, hi, g) in enumerate(plan):
-            q[i] = _lerp(vals[:, lo], vals[:, hi], g)
+            q[first + i] = _lerp(vals[:, lo], vals[:, hi], g)
     return mean, sd, rhat, q

@@ -45,6 +45,17 @@ def test_summary_of_one_shard_matches_numpy(pkg, rows, entries, chains):
     assert np.array_equal(q, q0)                            # exact order statistics, numpy's interpolation rule
 
 
+def test_long_probability_grids_run_as_several_selects(pkg):
+    """more than 16 probabilities (an equal-mass histogram): split into selects of at most 32 order statistics each"""
+    import torch
+    from bayes_js_b200.summary import summarise_block
+    from summary_ref import NumpyBlockReducer, numpy_summary
+    x = _block(11, 2, 97, 8)
+    probs = tuple(np.linspace(0, 1, 41))
+    _, _, _, q = summarise_block(NumpyBlockReducer(), torch.from_numpy(x), 11, 97, probs, False)
+    assert q.shape == (41, 2) and np.array_equal(q, numpy_summary(x, probs)[3])
+
+
 def test_shards_merge_exactly(pkg):
     import torch
     from bayes_js_b200.summary import RadixSelect, finalize_moments, merge_moment_records, quantile_targets
