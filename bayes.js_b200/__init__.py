@@ -8,7 +8,7 @@
 `mcmc` mirrors /root/reference/mcmc.js, `ld` mirrors /root/reference/distributions.js; the hot path runs in
 libamwg_b200.so (csrc/, C ABI in include/amwg.h).  There is no CPU fallback.
 """
-from . import _ffi, mcmc, summary, tracer   # noqa: F401
+from . import _ffi, mcmc, parallel, summary, tracer   # noqa: F401
 from . import distributions as ld           # noqa: F401
 from .tracer import JsThrow                 # noqa: F401
 

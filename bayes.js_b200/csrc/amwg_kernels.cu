@@ -22,12 +22,15 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 
 #include "../../include/amwg.h"
 #include "amwg_math.cuh"
 #include "amwg_ld.cuh"
+#include "amwg_tma.cuh"
 
 namespace amwg {
 
@@ -35,7 +38,7 @@ constexpr int kMaxColumns = 16;
 constexpr int kMaxParams = 16;       // substepper order is packed 4 bits per named parameter
 constexpr int kMaxDim0 = 256;        // top-level visit order of a multi-dim parameter (uint8 per entry)
 constexpr int kMaxDerived = 8;
-constexpr int kStack = 16;
+constexpr int kStack = 32;          // operand stack of the interpreter; validate_model rejects programs that need more
 #ifndef AMWG_THREADS
 #define AMWG_THREADS 128
 #endif
@@ -75,34 +78,6 @@ struct ModelDev {
   int variant_comps[AMWG_MAX_VARIANT_COMPS];
   int variant_logpost[1 << AMWG_MAX_VARIANT_COMPS];
   int variant_derived[1 << AMWG_MAX_VARIANT_COMPS];
-};
-
-struct ChainArrays {
-  double* state;          // [D][C]
-  double* pls;            // [D][C] prop_log_scale
-  double* psd;            // [D][C] exp(prop_log_scale): the proposal sd, recomputed only when pls changes (same bits as mcmc.js:578)
-  int* acc;               // [D][C] acceptance_count of the current batch
-  double* curr_lp;        // [C]   cached log_post(state)
-  double* tval;           // [n_terms][C] term cache: value of every value-term of log_post at the chain's current state
-  double* tcand;          // [n_terms][C] candidates written while a proposal is evaluated; committed on acceptance
-  double* bprop;          // [D][C] block steps: the proposal of every component of the block (its current value when out of bounds)
-  double* bcoin;          // [D][C] block steps: the accept uniform drawn for it (-1: proposal out of bounds, no uniform drawn)
-  unsigned short* vseq;   // [D][C] pre-evaluated statistics: the components in this sweep's visiting order
-  unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
-  unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
-  unsigned long long C;
-  unsigned long long first_chain;
-  unsigned long long seed;
-};
-
-struct SweepArgs {
-  long long n_sweeps;
-  long long sample_i0;     // index i of the first sweep within the current sample() call
-  long long thin;
-  int record;              // 0: burn, 1: sample
-  int n_monitor;
-  const int* monitor;      // global [n_monitor]
-  double* out;             // [row][monitor][chain]
 };
 
 struct Ctx {                       // lives in shared memory
@@ -159,32 +134,6 @@ struct EvalStateT<true> : EvalStateBase {
 };
 using EvalState = EvalStateT<true>;
 
-// ---- TMA 1-D bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
-  asm volatile(
-      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n}\n" ::"r"(
-          smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
-               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ double2 lds_f64x2(unsigned saddr) {
-  double2 v;
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
-  return v;
-}
-
 // Stage the model image and every data column that fits into shared memory; fill ctx. All threads call this.
 __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* smem, Ctx& ctx, unsigned long long* bar) {
   if (threadIdx.x == 0) {
@@ -221,80 +170,6 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
   __syncthreads();
   mbar_wait(bar, 0);
 }
-
-// ---- plates: the O(N) likelihood sums -----------------------------------------------------------------------------
-// sum_i (x_i - mean)^2 : 2 fp64-pipe instructions per point (DADD + DFMA), AMWG_NACC independent accumulators, eight points
-// per block read as four 16-byte warp-broadcast loads (ld.shared.v2.f64 when `saddr` != 0, i.e. the column sits in shared
-// memory; else the same loop over global/L2 addresses). AMWG_PREFETCH: the next block is loaded while the current one is summed.
-#ifndef AMWG_NACC
-#define AMWG_NACC 4
-#endif
-#ifndef AMWG_PREFETCH
-#define AMWG_PREFETCH 1
-#endif
-#if AMWG_NACC == 8
-#define AMWG_ACC8(P0, P1, P2, P3)                                                                              \
-  {                                                                                                            \
-    double d0 = P0.x - mean, d1 = P0.y - mean, d2 = P1.x - mean, d3 = P1.y - mean;                             \
-    double d4 = P2.x - mean, d5 = P2.y - mean, d6 = P3.x - mean, d7 = P3.y - mean;                             \
-    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);                     \
-    s4 = fma(d4, d4, s4); s5 = fma(d5, d5, s5); s6 = fma(d6, d6, s6); s7 = fma(d7, d7, s7);                     \
-  }
-#else
-#define AMWG_ACC8(P0, P1, P2, P3)                                                                              \
-  {                                                                                                            \
-    double d0 = P0.x - mean, d1 = P0.y - mean, d2 = P1.x - mean, d3 = P1.y - mean;                             \
-    double d4 = P2.x - mean, d5 = P2.y - mean, d6 = P3.x - mean, d7 = P3.y - mean;                             \
-    s0 = fma(d0, d0, s0); s1 = fma(d1, d1, s1); s2 = fma(d2, d2, s2); s3 = fma(d3, d3, s3);                     \
-    s0 = fma(d4, d4, s0); s1 = fma(d5, d5, s1); s2 = fma(d6, d6, s2); s3 = fma(d7, d7, s3);                     \
-  }
-#endif
-__device__ __forceinline__ double sum_sq_dev(const double* __restrict__ x, unsigned saddr, int n, double mean) {
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#if AMWG_NACC == 8
-  double s4 = 0.0, s5 = 0.0, s6 = 0.0, s7 = 0.0;
-#endif
-  int i = 0;
-  if ((reinterpret_cast<unsigned long long>(x) & 15ull) && n > 0) { double d = x[0] - mean; s3 = fma(d, d, s3); i = 1; }   // 16B-align the vector loads
-  const int nb = (n - i) >> 3;                 // blocks of eight points
-  if (nb > 0) {
-    if (saddr) {
-      unsigned a = saddr + 8u * (unsigned)i;
-#if AMWG_PREFETCH
-      double2 p0 = lds_f64x2(a), p1 = lds_f64x2(a + 16u), p2 = lds_f64x2(a + 32u), p3 = lds_f64x2(a + 48u);
-#pragma unroll 2
-      for (int b = 1; b < nb; ++b) {
-        a += 64u;
-        double2 q0 = lds_f64x2(a), q1 = lds_f64x2(a + 16u), q2 = lds_f64x2(a + 32u), q3 = lds_f64x2(a + 48u);
-        AMWG_ACC8(p0, p1, p2, p3)
-        p0 = q0; p1 = q1; p2 = q2; p3 = q3;
-      }
-      AMWG_ACC8(p0, p1, p2, p3)
-#else
-#pragma unroll 2
-      for (int b = 0; b < nb; ++b, a += 64u) {
-        double2 p0 = lds_f64x2(a), p1 = lds_f64x2(a + 16u), p2 = lds_f64x2(a + 32u), p3 = lds_f64x2(a + 48u);
-        AMWG_ACC8(p0, p1, p2, p3)
-      }
-#endif
-    } else {
-      const double2* g = reinterpret_cast<const double2*>(x + i);
-#pragma unroll 2
-      for (int b = 0; b < nb; ++b, g += 4) {
-        double2 p0 = g[0], p1 = g[1], p2 = g[2], p3 = g[3];
-        AMWG_ACC8(p0, p1, p2, p3)
-      }
-    }
-    i += nb << 3;
-  }
-  for (; i < n; ++i) { double d = x[i] - mean; s0 = fma(d, d, s0); }
-#if AMWG_NACC == 8
-  return ((s0 + s1) + (s2 + s3)) + ((s4 + s5) + (s6 + s7));
-#else
-  return (s0 + s1) + (s2 + s3);
-#endif
-}
-#undef AMWG_ACC8
 
 // ---- TMA tile ring: plates over a column that does not fit in shared memory ------------------------------------------------
 // Legal only when the whole CTA walks the plate together (ModelDev.phase_sync: every chain takes the same steps per sweep and
@@ -692,6 +567,22 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
   if (valid) a.curr_lp[chain] = lp0;
 }
 
+// log_post at the chains' CURRENT state, evaluated afresh with the full program (nothing is stored): what sampler.log_post()
+// returns for handles whose sweep kernel does not carry the value along (the run-time specialised sweep works on differences).
+__global__ void __launch_bounds__(kThreads) amwg_relp_kernel(ModelDev m, ChainArrays a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ Ctx ctx;
+  __shared__ __align__(8) unsigned long long bar;
+  stage_model(m, smem, ctx, &bar);
+  const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = tid < a.C;
+  if (!valid && !ctx.ring_saddr) return;
+  const unsigned long long chain = valid ? tid : a.C - 1;              // shadow threads keep a streamed plate CTA-uniform
+  EvalState es{a.state + chain, a.C, -1, 0.0};
+  const double lp = eval_logpost(ctx, es, logpost_pc(m, es));
+  if (valid) a.curr_lp[chain] = lp;
+}
+
 // ---- K1: n_sweeps Sampler.step()s per chain, samples recorded before each kept sweep --------------------------------
 // Phase synchronisation: when every chain takes the same number of steps per sweep (all parameters scalar, or a single
 // parameter), the CTA runs propose / evaluate / accept in lock step (__syncthreads between phases). Warps that share a
@@ -1064,10 +955,6 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
   }
 }
 
-}  // namespace amwg
-#include "amwg_wide.cuh"
-namespace amwg {
-
 // ---- K2: Roberts-Rosenthal batch update of prop_log_scale (mcmc.js:538-550), a follow-on kernel -----------------------
 struct AdaptArgs {
   int c0, n;
@@ -1171,8 +1058,12 @@ struct amwg_sampler {
   double* d_out = nullptr; size_t d_out_bytes = 0;
   int* d_monitor = nullptr; int d_monitor_cap = 0;
   long long launches = 0;
-  int chains_per_thread = 1;                  // 1: amwg_sweep_kernel; 2 / 4: amwg_sweep_kernel_wide<W>
   double last_sweep_ms = 0.0;
+  // run-time specialised sweep (amwg_jit.cuh): active when jit_kernel != nullptr
+  cudaKernel_t jit_kernel = nullptr;
+  unsigned jit_smem = 0;
+  int jit_threads = 0;
+  std::string jit_note = "not attempted";
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
 };
 
@@ -1197,6 +1088,16 @@ static int dev_alloc(amwg_sampler* s, size_t n, T** out) {
 }
 
 static unsigned pad16(size_t b) { return (unsigned)((b + 15) / 16 * 16); }
+
+#include "amwg_jit.cuh"
+
+// arguments of the run-time specialised sweep (amwg_jit_kernel.cuh: struct JitArgs, same layout)
+struct JitArgsHost {
+  ChainArrays a;
+  SweepArgs sa;
+  const double* col[kMaxColumns];
+  const unsigned char* adapting;
+};
 
 static int validate_model(const amwg_model* md) {
   if (!md) return fail("amwg_create: model is NULL");
@@ -1241,6 +1142,72 @@ static int validate_model(const amwg_model* md) {
   for (int k = 0; k < md->n_fold; ++k)
     if (md->fold_prog[k] < 0 || md->fold_prog[k] >= md->n_code || md->fold_dst[k] < 0 || md->fold_dst[k] >= md->n_consts)
       return fail("amwg_create: constant-folding table out of range");
+  // every program: well-formed words, operand stack within the interpreter's, every index inside its table
+  std::vector<int> progs;
+  progs.push_back(md->logpost_prog);
+  if (md->n_derived > 0) progs.push_back(md->derived_prog);
+  for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v) {
+    progs.push_back(md->variant_logpost[v]);
+    if (md->variant_derived && md->variant_derived[v] >= 0) progs.push_back(md->variant_derived[v]);
+  }
+  if (md->comp_prog && md->n_terms > 0) for (int c = 0; c < md->n_comp; ++c) progs.push_back(md->comp_prog[c]);
+  if (md->comp_prog && md->n_terms > 0 && md->stat_prog >= 0) progs.push_back(md->stat_prog);
+  for (int k = 0; k < md->n_fold; ++k) progs.push_back(md->fold_prog[k]);
+  const int n_slots = (md->comp_prog && md->n_terms > 0) ? md->n_terms : 0;
+  for (int pc : progs) {
+    std::vector<jit::Insn> ins;
+    std::string err;
+    int depth = 0;
+    if (!jit::decode_program(md, pc, ins, &depth, err)) return fail("amwg_create: malformed program: " + err);
+    if (depth > kStack)
+      return fail("log_post nests expressions " + std::to_string(depth) + " deep; the device's operand stack holds " + std::to_string(kStack));
+    int loop_n = 0;
+    for (const jit::Insn& in : ins) {
+      for (int k = 0; k < 4; ++k) {
+        if (in.mode[k] == AMWG_MODE_CONST && (in.inl[k] < 0 || in.inl[k] >= md->n_consts)) return fail("amwg_create: constant index out of range");
+        if (in.mode[k] == AMWG_MODE_COMP && (in.inl[k] < 0 || in.inl[k] >= D)) return fail("amwg_create: component index out of range");
+      }
+      switch (in.op) {
+        case AMWG_OP_CONST: if (in.a >= md->n_consts) return fail("amwg_create: constant index out of range"); break;
+        case AMWG_OP_COMP: if (in.a >= D) return fail("amwg_create: component index out of range"); break;
+        case AMWG_OP_DATA:
+          if (in.a >= md->n_columns || in.extra[0] < 0 || in.extra[0] >= md->columns[in.a].n) return fail("amwg_create: data index out of range");
+          break;
+        case AMWG_OP_LOOP_BEGIN:
+          if (in.a >= md->n_plates) return fail("amwg_create: plate index out of range");
+          loop_n = md->plates[in.a].n;
+          break;
+        case AMWG_OP_DATA_I: case AMWG_OP_COMP_I: {
+          if (in.a >= md->n_columns) return fail("amwg_create: data column out of range");
+          const long long off = in.extra[0], stride = in.extra[1], last = off + stride * (long long)std::max(loop_n - 1, 0);
+          if (off < 0 || off >= md->columns[in.a].n || last < 0 || last >= md->columns[in.a].n) return fail("amwg_create: plate walks past the end of a data column");
+          if (in.op == AMWG_OP_COMP_I)           // state[base + data[i]]: JS would read `undefined` outside the array; refuse instead of reading past the state
+            for (int i = 0; i < loop_n; ++i) {
+              const double v = md->columns[in.a].values[off + stride * i];
+              if (!(v == std::floor(v)) || in.extra[2] + v < 0 || in.extra[2] + v >= D) return fail("log_post indexes a parameter array with a data value outside its bounds");
+            }
+          break;
+        }
+        case AMWG_OP_PLATE: case AMWG_OP_PLATE_SS: case AMWG_OP_NORM_SS: {
+          if (in.a >= md->n_plates) return fail("amwg_create: plate index out of range");
+          const amwg_plate& pl = md->plates[in.a];
+          for (int j = 0; j < 3; ++j) if (pl.col[j] >= md->n_columns) return fail("amwg_create: plate column out of range");
+          if (in.op != AMWG_OP_NORM_SS && pl.kind != AMWG_PLATE_GENERIC) {
+            if (pl.col[0] < 0 || pl.iparam[2] < 0 || (long long)pl.iparam[2] + pl.n > md->columns[pl.col[0]].n) return fail("amwg_create: plate runs past its data column");
+            if ((pl.kind == AMWG_PLATE_NORM_GROUPED || pl.kind == AMWG_PLATE_POIS_LOGLIN) && (pl.iparam[0] < 0 || pl.iparam[1] < 0 || pl.iparam[0] + pl.iparam[1] > D))
+              return fail("amwg_create: plate parameter range out of bounds");
+          }
+          if (in.op == AMWG_OP_PLATE_SS && (in.extra[0] < 0 || in.extra[0] >= n_slots)) return fail("amwg_create: statistic slot out of range");
+          break;
+        }
+        case AMWG_OP_CACHED: case AMWG_OP_CAND: if (in.a >= n_slots) return fail("amwg_create: cache slot out of range"); break;
+        case AMWG_OP_ACC_RANGE: if (in.extra[0] < 0 || in.a + in.extra[0] > n_slots) return fail("amwg_create: ACC_RANGE out of range"); break;
+        case AMWG_OP_STORE: if (in.a >= std::max(md->n_derived, 1)) return fail("amwg_create: derived index out of range"); break;
+        default: break;
+      }
+      if (in.term >= 0 && n_slots > 0 && in.term >= n_slots) return fail("amwg_create: term id out of range");
+    }
+  }
   return 0;
 }
 
@@ -1265,6 +1232,72 @@ extern "C" void amwg_destroy(amwg_sampler* s) {
 }
 
 static unsigned grid_for(unsigned long long C, int threads) { return (unsigned)((C + threads - 1) / threads); }
+
+// -0.5 * Math.log(2 * Math.PI) with the DEVICE's log (the value every kernel uses for the factorised Normal plates)
+static int device_norm_c0(int device, double* out) {
+  const double two_pi = 2 * AMWG_JS_PI;
+  double lg = 0.0;
+  if (amwg_primitive_eval(0, &two_pi, 1, 0, 0, &lg, device)) return -1;
+  *out = -0.5 * lg;
+  return 0;
+}
+
+// Try to replace the interpreter sweep of this handle by a kernel specialised for its model (amwg_jit.cuh). Never fatal: on any
+// failure the handle keeps the interpreter kernels and s->jit_note says why.
+static void try_jit(amwg_sampler* s, const amwg_model* md) {
+  s->jit_note = "off";
+  int want = -1;                                        // -1: when it pays (many chains), 0: never, 1: whenever the model is eligible
+  if (const char* e = getenv("AMWG_JIT")) want = atoi(e);
+  if (want == 0) { s->jit_note = "disabled (AMWG_JIT=0)"; return; }
+  if (s->m.stat_prog < 0) { s->jit_note = "the model does not run the statistics sweep"; return; }
+  if (want < 0 && s->a.C < 4096) { s->jit_note = "fewer than 4096 chains: the interpreter kernels start faster than a compilation"; return; }
+  std::vector<double> consts((size_t)std::max(md->n_consts, 1), 0.0);
+  if (md->n_consts > 0 &&
+      cudaMemcpy(consts.data(), s->m.image + s->m.off_consts, sizeof(double) * (size_t)md->n_consts, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    s->jit_note = "could not read the folded constants back"; cudaGetLastError(); return;
+  }
+  double c0 = 0.0;
+  if (device_norm_c0(s->device, &c0)) { s->jit_note = "could not evaluate the Normal constant on the device"; return; }
+  cudaDeviceProp prop{};
+  if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { s->jit_note = "cudaGetDeviceProperties failed"; cudaGetLastError(); return; }
+  jit::Source src;
+  std::string why = jit::build_source(md, consts, s->a.C, prop.multiProcessorCount, c0, src);
+  if (!why.empty()) { s->jit_note = "not specialised: " + why; return; }
+  if (src.plan.smem_bytes > (unsigned)prop.sharedMemPerBlockOptin) { s->jit_note = "not specialised: shared-memory plan does not fit"; return; }
+  const unsigned long long key = jit::fnv1a(src.generated, jit::fnv1a(src.prelude));
+  jit::Loaded ld;
+  {
+    std::lock_guard<std::mutex> lock(jit::g_cache_mu);
+    auto it = jit::g_cache.find({s->device, key});
+    if (it != jit::g_cache.end()) ld = it->second;
+  }
+  bool disk = false;
+  if (!ld.kernel) {
+    std::vector<char> cubin;
+    std::string log;
+    std::string e = jit::get_cubin(src, cubin, log, &disk);
+    if (!e.empty()) { s->jit_note = "compilation failed: " + e + (log.empty() ? "" : "\n" + log); return; }
+    if (cudaLibraryLoadData(&ld.lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) != cudaSuccess ||
+        cudaLibraryGetKernel(&ld.kernel, ld.lib, "amwg_jit_sweep") != cudaSuccess) {
+      s->jit_note = std::string("loading the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+      return;
+    }
+    std::lock_guard<std::mutex> lock(jit::g_cache_mu);
+    jit::g_cache[{s->device, key}] = ld;
+  }
+  if (cudaFuncSetAttribute((const void*)ld.kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)src.plan.smem_bytes) != cudaSuccess) {
+    s->jit_note = std::string("cudaFuncSetAttribute on the compiled kernel failed: ") + cudaGetErrorString(cudaGetLastError());
+    return;
+  }
+  s->jit_kernel = ld.kernel;
+  s->jit_smem = src.plan.smem_bytes;
+  s->jit_threads = src.plan.threads;
+  char note[256];
+  snprintf(note, sizeof note, "specialised sweep: %d threads x %d CTAs/SM, %u B shared memory, %d resident column(s)%s%s%s", src.plan.threads, src.plan.minblocks,
+           src.plan.smem_bytes, src.plan.n_res, src.plan.stream_col >= 0 ? ", one streamed column" : "", src.plan.ws_smem ? ", working set in shared memory" : "",
+           disk ? " (cubin from the disk cache)" : "");
+  s->jit_note = note;
+}
 
 extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t first_chain, uint64_t seed, int device,
                            amwg_sampler** out) {
@@ -1370,16 +1403,11 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     if (use) { m.scratch_smem_off = (int)pad16(smem_used); smem_used = (unsigned)(pad16(smem_used) + need); }
   }
   s->smem_bytes = smem_used;
-  // chains per thread: 1. The W = 2 / 4 variants (amwg_wide.cuh) execute 22 % fewer instructions per chain-step but need 168
-  // registers (12 warps/SM) and measure 0.77x / 0.61x on config 2 (profiles/r01w); AMWG_CHAINS_PER_THREAD selects them for experiments.
-  s->chains_per_thread = 1;
-  if (const char* e = getenv("AMWG_CHAINS_PER_THREAD")) { int w = atoi(e); if (w == 1 || w == 2 || w == 4) s->chains_per_thread = w; }
-  if (cudaFuncSetAttribute(amwg_sweep_kernel_wide<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
-      cudaFuncSetAttribute(amwg_sweep_kernel_wide<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
-      cudaFuncSetAttribute(amwg_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+  if (cudaFuncSetAttribute(amwg_sweep_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_sweep_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_stat_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_init_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
+      cudaFuncSetAttribute(amwg_relp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_fold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess ||
       cudaFuncSetAttribute(amwg_derived_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget) != cudaSuccess)
     return bail(fail("cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed"));
@@ -1401,7 +1429,6 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     if (dev_alloc(s, 2 * TC + 2 * DC, &a.tval)) return bail(-1);
     a.tcand = a.tval + TC; a.bprop = a.tcand + TC; a.bcoin = a.bprop + DC;
     if (m.stat_prog >= 0 && dev_alloc(s, DC, &a.vseq)) return bail(-1);
-    s->chains_per_thread = 1;            // the experimental wide kernel evaluates the full program only
   }
 
   double* d_init = nullptr; double* d_pls0 = nullptr;
@@ -1420,6 +1447,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
   if (e != cudaSuccess) return bail(fail(std::string("amwg_init_kernel: ") + cudaGetErrorString(e)));
+  try_jit(s, md);
   *out = s;
   return 0;
 }
@@ -1450,10 +1478,12 @@ static int run_sweeps(amwg_sampler* s, long long n, int record, long long thin, 
       s->ev_pool.emplace_back(e0, e1);
     }
     CUDA_TRY(cudaEventRecord(s->ev_pool[n_events].first, s->stream));
-    if (s->chains_per_thread == 2) {
-      amwg_sweep_kernel_wide<2><<<grid_for((C + 1) / 2, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
-    } else if (s->chains_per_thread == 4) {
-      amwg_sweep_kernel_wide<4><<<grid_for((C + 3) / 4, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
+    if (s->jit_kernel) {
+      JitArgsHost ja{};
+      ja.a = s->a; ja.sa = sa; ja.adapting = s->d_adapting;
+      for (int k = 0; k < kMaxColumns; ++k) ja.col[k] = k < s->m.n_columns ? s->m.col_global[k] : nullptr;
+      void* kargs[] = {&ja};
+      CUDA_TRY(cudaLaunchKernel((const void*)s->jit_kernel, dim3(grid_for(C, s->jit_threads)), dim3((unsigned)s->jit_threads), kargs, s->jit_smem, s->stream));
     } else {
       const int threads = s->m.phase_sync ? kSyncThreads : kThreads;
       if (s->m.stat_prog >= 0) amwg_stat_sweep_kernel<<<grid_for(C, kSyncThreads), kSyncThreads, s->smem_bytes, s->stream>>>(s->m, s->a, sa);
@@ -1597,6 +1627,11 @@ extern "C" int amwg_get_state(amwg_sampler* s, double* host_out) {
 extern "C" int amwg_get_log_post(amwg_sampler* s, double* host_out) {
   if (!s || !host_out) return fail("amwg_get_log_post: NULL argument");
   CUDA_TRY(cudaSetDevice(s->device));
+  if (s->jit_kernel) {          // the specialised sweep steps on differences: evaluate log_post at the current state now
+    amwg_relp_kernel<<<grid_for(s->a.C, kThreads), kThreads, s->smem_bytes, s->stream>>>(s->m, s->a);
+    CUDA_TRY(cudaGetLastError());
+    s->launches++;
+  }
   CUDA_TRY(cudaMemcpyAsync(host_out, s->a.curr_lp, sizeof(double) * (size_t)s->a.C, cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
   return 0;
@@ -1622,6 +1657,35 @@ extern "C" int amwg_info(amwg_sampler* s, double* scalars, double* prop_log_scal
   if (prop_log_scale) CUDA_TRY(cudaMemcpyAsync(prop_log_scale, s->a.pls, sizeof(double) * DC, cudaMemcpyDeviceToHost, s->stream));
   if (acceptance_count) CUDA_TRY(cudaMemcpyAsync(acceptance_count, s->a.acc, sizeof(int) * DC, cudaMemcpyDeviceToHost, s->stream));
   CUDA_TRY(cudaStreamSynchronize(s->stream));
+  return 0;
+}
+
+// 1 when the handle runs the run-time specialised sweep, 0 when it runs the interpreter kernels; `note` says what was built or why not
+extern "C" int amwg_jit_status(const amwg_sampler* s, char* note, int64_t cap) {
+  if (!s) return 0;
+  if (note && cap > 0) { snprintf(note, (size_t)cap, "%s", s->jit_note.c_str()); }
+  return s->jit_kernel ? 1 : 0;
+}
+
+// Generate and compile the specialised sweep of `model` without a GPU (NVRTC targets sm_100a from any host): 0 = compiled,
+// 1 = the model is not eligible (reason in `log`), -1 = generation or compilation failed (message in `log`). `src`, when given,
+// receives the generated source. Constants that the device would fold at create are left as they are in the model.
+extern "C" int amwg_jit_compile_check(const amwg_model* md, uint64_t n_chains, char* log, int64_t log_cap, char* src_out, int64_t src_cap) {
+  auto put = [](char* dst, int64_t cap, const std::string& s) { if (dst && cap > 0) snprintf(dst, (size_t)cap, "%s", s.c_str()); };
+  if (validate_model(md)) { put(log, log_cap, g_last_error); return -1; }
+  std::vector<double> consts(md->consts, md->consts + md->n_consts);
+  if (consts.empty()) consts.push_back(0.0);
+  jit::Source src;
+  std::string why = jit::build_source(md, consts, n_chains ? n_chains : 1, 148, -0.9189385332046727, src);
+  if (!why.empty()) { put(log, log_cap, why); return 1; }
+  put(src_out, src_cap, src.prelude + src.generated);
+  std::vector<char> cubin;
+  std::string clog;
+  std::string e = jit::compile(src, cubin, clog);
+  if (!e.empty()) { put(log, log_cap, e + "\n" + clog); return -1; }
+  char info[160];
+  snprintf(info, sizeof info, "ok: cubin %zu bytes, %d threads x %d CTAs/SM, %u B shared memory", cubin.size(), src.plan.threads, src.plan.minblocks, src.plan.smem_bytes);
+  put(log, log_cap, std::string(info) + (clog.size() > 1 ? "\n" + clog : ""));
   return 0;
 }
 
@@ -1665,3 +1729,4 @@ extern "C" int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uin
 }
 
 #include "amwg_summary.cuh"
+#include "amwg_peak.cuh"

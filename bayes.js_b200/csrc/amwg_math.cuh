@@ -5,9 +5,17 @@
 // operation, as in a JS engine.  Fused multiply-adds appear only where written as fma() (the
 // factorised likelihood plates in amwg_kernels.cu).
 #pragma once
+#ifdef __CUDACC_RTC__
+// run-time compilation (NVRTC, amwg_jit.cuh): no host headers; the few names this file needs from them
+typedef unsigned int uint32_t;
+typedef unsigned long long uint64_t;
+#define CUDART_INF __longlong_as_double(0x7ff0000000000000LL)
+#define CUDART_NAN __longlong_as_double(0xfff8000000000000LL)
+#else
 #include <cstdint>
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#endif
 
 namespace amwg {
 

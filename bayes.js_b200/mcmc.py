@@ -420,6 +420,9 @@ class AmwgSampler(Sampler):
         m.variant_derived = vder.ctypes.data_as(C.POINTER(C.c_int32))
         self._model_keepalive = (prm, init, opts, code, consts, cols, plates, fold_prog, fold_dst, vcomps, vlp, vder, m)
         L = _ffi.lib()
+        if get_option("_model_only", self.options, False):       # tests: lower the model, do not touch a device
+            self._model = m
+            return
         h = C.c_void_p()
         rc = L.amwg_create(C.byref(m), self.local_chains, self.first_chain, self.seed, self.device, C.byref(h))
         if rc != 0:
@@ -627,7 +630,24 @@ class AmwgSampler(Sampler):
         return float(_ffi.lib().amwg_last_sweep_kernel_ms(self._handle))
 
     def program_summary(self) -> List[str]:
-        return list(self._program.summary)
+        return list(self._program.summary) + [self.jit_status()[1]]
+
+    def jit_status(self):
+        """(active, note): does this handle step with a kernel specialised for its model at run time (csrc/amwg_jit.cuh)?"""
+        if not getattr(self, "_handle", None):
+            return False, "no device handle"
+        buf = C.create_string_buffer(4096)
+        on = _ffi.lib().amwg_jit_status(self._handle, buf, len(buf))
+        return bool(on), buf.value.decode("utf-8", "replace")
+
+    def jit_compile_check(self, n_chains=None):
+        """Generate and compile the specialised sweep of this model without running it (works without a GPU).
+        -> (rc, message, source): rc 0 compiled, 1 model not eligible, -1 error."""
+        log = C.create_string_buffer(1 << 16)
+        src = C.create_string_buffer(1 << 20)
+        m = self._model_keepalive[-1]
+        rc = _ffi.lib().amwg_jit_compile_check(C.byref(m), int(n_chains or self.n_chains), log, len(log), src, len(src))
+        return rc, log.value.decode("utf-8", "replace"), src.value.decode("utf-8", "replace")
 
 
 class _PinnedPool:

@@ -243,9 +243,19 @@ class ParamVec:
         for d in self._shape[1:]: inner *= d
         if isinstance(i, Sym):
             if i.op == "DATA":                      # concrete data value used as an index (mu[g[i]])
-                i = int(self._t.columns[i.val[0]][i.val[1]])
+                v = float(self._t.columns[i.val[0]][i.val[1]])
+                if v != math.floor(v):
+                    return Sym("CONST", (), float("nan"))          # JS: a[1.5] is undefined
+                i = int(v)
             elif i.op == "DATA_I" and len(self._shape) == 1:
                 col, off, stride, pid = i.val
+                n = self._t.plate_sizes.get(pid, 0)
+                idx = self._t.columns[col][off: off + stride * max(n, 1): stride]
+                # JS reads `undefined` outside the array (-> NaN, the chain never moves); on the device the read would alias another
+                # parameter or leave the state array, so such a model is refused
+                if idx.size and (np.any(idx != np.floor(idx)) or idx.min() < 0 or idx.max() >= self._shape[0]):
+                    raise JsThrow("log_post indexes a parameter array of length %d with data values outside its bounds [%g, %g]"
+                                  % (self._shape[0], float(idx.min()), float(idx.max())))
                 return Sym("COMP_I", (), (col, off, stride, self._c0, pid))
             else:
                 raise JsThrow("a parameter array can only be indexed by numbers or by data values")
@@ -939,13 +949,12 @@ class Lowering:
         parameter; enough plate points for one data pass per sweep (instead of one per step) to matter."""
         terms = self._terms
         plates = [tr for tr in terms if "plate_kind" in tr]
-        mode = os.environ.get("AMWG_STAT_LOWERING", "1")              # 0: never, 2: whenever eligible (A/B runs, tests), 1: when it pays
+        mode = os.environ.get("AMWG_STAT_LOWERING", "1")              # 0: never (A/B runs, tests); otherwise whenever eligible
         if mode == "0":
             return False
-        # Measured on B200 (DESIGN.md): with two components the sweep saves one of two data passes but pays for it in bookkeeping
-        # (2.4e9 vs 2.5e9 draws/s on the headline model); from three components on it wins.
-        if mode != "2" and self.n_comp <= 2:
-            return False
+        # Round 1 kept two-component models on the full program (the interpreter's O(1) steps cost what the saved data pass gained:
+        # 2.4e9 vs 2.5e9 draws/s on the headline model). The sweep is now specialised per model at run time (csrc/amwg_jit.cuh),
+        # which removes that bookkeeping, so every eligible model is lowered this way.
         if not plates or any(ptype == "binary" for _, _, ptype in self.param_ranges) or not self.param_ranges:
             return False
         if any(tr["plate_kind"] != PLATE_NORM_IID or len(tr["mean_deps"]) != 1 for tr in plates):

@@ -274,6 +274,21 @@ AMWG_API int amwg_summary_moments(int device, const double* dev_samples, int64_t
 AMWG_API int amwg_summary_digit_hist(int device, const double* dev_samples, int64_t rows, int32_t entries, int64_t chains, int32_t pass,
                                      const uint64_t* dev_prefix, int32_t n_prefix, uint64_t* dev_counts);
 
+/* ---- run-time specialisation ----------------------------------------------------------------------------------------------
+ * For models that run the statistics sweep (stat_prog) amwg_create generates CUDA source from the model's programs, compiles it
+ * for sm_100a with NVRTC and steps with that kernel instead of the bytecode interpreter (csrc/amwg_jit.cuh; AMWG_JIT=0 in the
+ * environment keeps the interpreter, AMWG_JIT=1 specialises whatever the number of chains). amwg_jit_status: 1 when the handle
+ * runs a specialised kernel, with a one-line description (or the reason it does not) in `note`. amwg_jit_compile_check: generate
+ * and compile without a GPU (0 compiled, 1 model not eligible, -1 error; message in `log`, generated source in `src`). */
+AMWG_API int amwg_jit_status(const amwg_sampler* s, char* note, int64_t cap);
+AMWG_API int amwg_jit_compile_check(const amwg_model* model, uint64_t n_chains, char* log, int64_t log_cap, char* src, int64_t src_cap);
+
+/* ---- measurement ---------------------------------------------------------------------------------------------------------
+ * The binding roof of this path is the non-tensor fp64 pipe (DADD + DFMA per data point), which MEASURED_PEAKS.json does not
+ * hold: amwg_peak_fp64 measures it (TFLOP/s, 2 flop per DFMA; best of `reps` launches of a DFMA-chain kernel that fills every SM,
+ * CUDA events on the launching stream). bench.py reports roofline fractions against this number, taken in the same process. */
+AMWG_API int amwg_peak_fp64(int device, int reps, double* tflops_out, double* ms_out);
+
 #ifdef __cplusplus
 }
 #endif

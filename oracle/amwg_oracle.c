@@ -719,3 +719,42 @@ ORC_API void orc_run_chains(int n_params, const orc_param* params, const double*
     orc_destroy(s);
   }
 }
+
+/* The same, on `n_threads` host threads (bench.py --impl reference: the reference is single-threaded JavaScript, mcmc.js has no
+ * parallelism; independent chains are the only way to occupy a many-core host with it). Chains are dealt out in contiguous
+ * blocks; every chain is the same computation as in orc_run_chains, so the output does not depend on n_threads. */
+#include <pthread.h>
+typedef struct {
+  int n_params; const orc_param* params; const double* init; const orc_comp_options* opts; int n_derived; orc_logpost_fn fn;
+  const void* data; uint64_t seed, chain0; int64_t c_lo, c_hi, n_burn, n_sample, thin; const int32_t* monitor; int n_monitor; double* out;
+} orc_mt_job;
+static void* orc_mt_worker(void* arg) {
+  orc_mt_job* j = (orc_mt_job*)arg;
+  int64_t rows = (j->n_sample + j->thin - 1) / j->thin;
+  if (j->c_hi > j->c_lo)
+    orc_run_chains(j->n_params, j->params, j->init, j->opts, j->n_derived, j->fn, j->data, j->seed, j->chain0 + (uint64_t)j->c_lo,
+                   j->c_hi - j->c_lo, j->n_burn, j->n_sample, j->thin, j->monitor, j->n_monitor,
+                   j->out ? j->out + (size_t)j->c_lo * (size_t)rows * (size_t)j->n_monitor : NULL);
+  return NULL;
+}
+ORC_API int orc_run_chains_mt(int n_params, const orc_param* params, const double* init, const orc_comp_options* opts,
+                              int n_derived, orc_logpost_fn fn, const void* data, uint64_t seed,
+                              uint64_t chain0, int64_t n_chains, int64_t n_burn, int64_t n_sample, int64_t thin,
+                              const int32_t* monitor, int n_monitor, double* out, int n_threads) {
+  if (n_threads < 1) n_threads = 1;
+  if ((int64_t)n_threads > n_chains) n_threads = (int)n_chains;
+  pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)n_threads);
+  orc_mt_job* jobs = (orc_mt_job*)malloc(sizeof(orc_mt_job) * (size_t)n_threads);
+  int started = 0;
+  for (int t = 0; t < n_threads; t++) {
+    orc_mt_job j = { n_params, params, init, opts, n_derived, fn, data, seed, chain0,
+                     n_chains * t / n_threads, n_chains * (t + 1) / n_threads, n_burn, n_sample, thin, monitor, n_monitor, out };
+    jobs[t] = j;
+    if (pthread_create(&th[t], NULL, orc_mt_worker, &jobs[t]) != 0) break;
+    started++;
+  }
+  for (int t = 0; t < started; t++) pthread_join(th[t], NULL);
+  for (int t = started; t < n_threads; t++) orc_mt_worker(&jobs[t]);      /* could not start a thread: run its block here */
+  free(th); free(jobs);
+  return started;
+}

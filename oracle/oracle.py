@@ -90,6 +90,8 @@ def lib():
     L.orc_substepper_order.restype = None; L.orc_substepper_order.argtypes = [vp, vp]
     L.orc_run_chains.restype = None
     L.orc_run_chains.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, vp, u64, u64, i64, i64, i64, i64, vp, C.c_int, vp]
+    L.orc_run_chains_mt.restype = C.c_int
+    L.orc_run_chains_mt.argtypes = [C.c_int, vp, vp, vp, C.c_int, vp, vp, u64, u64, i64, i64, i64, i64, vp, C.c_int, vp, C.c_int]
     _lib = L
     return L
 
@@ -308,7 +310,7 @@ class OracleSampler:
 
 def run_model(model: str, data, params: Dict[str, dict], chains: int = 1, seed: int = 0, burn: int = 0, sample: int = 0,
               thin: int = 1, first_chain: int = 0, comp_options: Optional[Dict[str, dict]] = None,
-              monitor: Optional[List[str]] = None) -> Dict[str, np.ndarray]:
+              monitor: Optional[List[str]] = None, threads: int = 1) -> Dict[str, np.ndarray]:
     """`chains` independent oracle chains of a built-in model; output shaped like mcmc.AmwgSampler.sample():
     [rows, *dim] for one chain, [rows, chains, *dim] otherwise."""
     L = lib()
@@ -332,9 +334,13 @@ def run_model(model: str, data, params: Dict[str, dict], chains: int = 1, seed: 
     mon = np.asarray(ent, dtype=np.int32)
     rows = (sample + thin - 1) // thin if sample > 0 else 0
     out = np.empty((chains, max(rows, 1), len(ent)))
-    L.orc_run_chains(len(cp), C.cast(prm, C.c_void_p), init.ctypes.data, C.cast(opts, C.c_void_p), len(derived),
-                     C.cast(cfn, C.c_void_p), C.cast(C.pointer(st), C.c_void_p) if st is not None else None,
-                     seed, first_chain, chains, burn, sample, thin, mon.ctypes.data, len(ent), out.ctypes.data)
+    args = (len(cp), C.cast(prm, C.c_void_p), init.ctypes.data, C.cast(opts, C.c_void_p), len(derived),
+            C.cast(cfn, C.c_void_p), C.cast(C.pointer(st), C.c_void_p) if st is not None else None,
+            seed, first_chain, chains, burn, sample, thin, mon.ctypes.data, len(ent), out.ctypes.data)
+    if threads > 1:
+        L.orc_run_chains_mt(*args, int(threads))          # the C call releases the GIL; chains are dealt out to pthreads inside
+    else:
+        L.orc_run_chains(*args)
     out = out[:, :rows, :]
     res = {}
     for nm in names:
@@ -346,9 +352,9 @@ def run_model(model: str, data, params: Dict[str, dict], chains: int = 1, seed: 
     return res
 
 
-def time_model(model: str, data, params, chains: int, burn: int, sample: int, seed: int = 0) -> float:
-    """Wall seconds of `chains` sequential oracle chains (bench.py's CPU baseline; single thread)."""
+def time_model(model: str, data, params, chains: int, burn: int, sample: int, seed: int = 0, threads: int = 1) -> float:
+    """Wall seconds of `chains` oracle chains on `threads` host threads (bench.py's CPU baseline / reference arm)."""
     import time
     t0 = time.perf_counter()
-    run_model(model, data, params, chains=chains, seed=seed, burn=burn, sample=sample)
+    run_model(model, data, params, chains=chains, seed=seed, burn=burn, sample=sample, threads=threads)
     return time.perf_counter() - t0

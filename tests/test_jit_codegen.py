@@ -1,0 +1,113 @@
+"""Run-time specialisation (csrc/amwg_jit.cuh), CPU side: the generated CUDA source of eligible models compiles for sm_100a
+with NVRTC (no GPU needed), ineligible models say why, and malformed programs are refused by amwg_create's validation."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import models
+
+
+def _model_only(pkg, params, log_post, data, chains=1 << 16, **opts):
+    o = {"chains": chains, "_model_only": True}
+    o.update(opts)
+    return pkg.mcmc.AmwgSampler(params, log_post, data, o)
+
+
+def test_headline_model_specialises_and_compiles(pkg):
+    from conftest import config2_data
+    s = _model_only(pkg, models.PARAMS_NORM, models.norm_post_readme(pkg.ld), config2_data().tolist(), chains=1 << 20)
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "ok: cubin" in msg and "0 bytes spill stores" in msg
+    # two component classes (mu: prior + plate at the candidate statistic; sigma: prior + plate at the committed one), no interpreter
+    assert "switch (JCLS[c])" in src and "case 1:" in src and "js_exp(dl) > coin" in src
+    assert "#define JWS_SMEM 1" in src and "#define JN_RSTAT 1" in src and "#define JSTREAM 0" in src
+
+
+def test_hierarchical_model_classes_loops_and_streaming(pkg):
+    J, per = 64, 1024
+    g = np.repeat(np.arange(J), per)
+    y = np.random.default_rng(0).normal(100, 5, J * per)
+    P = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
+    s = _model_only(pkg, P, models.hier_norm_post(pkg.ld), {"y": y, "g": g.astype(float)})
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "0 bytes spill stores" in msg
+    # the 64 group means are ONE class (indices from tables), sigma's 64 plate terms are a loop, y (512 KB) streams through the ring
+    assert "const int m = JMEM[c];" in src and "for (int j = 0; j < 63; ++j)" in src
+    assert "#define JSTREAM 1" in src and "#define JN_SSTAT 64" in src and "#define JS_TOTAL 65536" in src
+    # a grid that fills 148 SMs evenly: 2^16 chains -> 293 CTAs of 224 threads, two per SM
+    assert "#define JTHREADS 224" in src and "#define JMINB 2" in src
+
+
+def test_expression_means_and_derived_quantities(pkg):
+    ld = pkg.ld
+
+    def lp(state, d):
+        out = 0
+        out += ld.norm(state.a, 0, 10)
+        out += ld.gamma(state.s, 2, 0.5)
+        for i in range(len(d)):
+            out += ld.norm(d[i], state.a * 2 + 1, state.s)
+        state.prec = 1 / (state.s * state.s)
+        return out
+    P = {"a": {"type": "real"}, "s": {"type": "real", "lower": 0}}
+    s = _model_only(pkg, P, lp, list(np.random.default_rng(1).normal(3, 1, 200)))
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "jit_derived" in src and "ld_gamma(" in src and "sum_sq_dev(" in src.split("jit_stat_extra")[1]
+
+
+def test_ineligible_models_keep_the_interpreter(pkg):
+    y = (np.random.default_rng(2).random(64) < 0.5).astype(float)
+    s = _model_only(pkg, models.PARAMS_SPIKE, models.spike_bern(pkg.ld, pkg.mcmc), {"x": y.tolist()})
+    rc, msg, _ = s.jit_compile_check()
+    assert rc == 1 and "no pre-evaluated statistics" in msg
+    from conftest import config2_data
+    s = _model_only(pkg, models.PARAMS_NORM, models.norm_post_readme(pkg.ld), config2_data().tolist(), faithful=True)
+    assert s.jit_compile_check()[0] == 1
+
+
+def test_deeply_nested_expressions_are_refused_not_corrupted(pkg):
+    """the interpreter's operand stack is fixed; a program that needs more must be rejected by validation."""
+    ld, mcmc = pkg.ld, pkg.mcmc
+
+    def deep(state, d):
+        e = state.x
+        for k in range(40):
+            e = 1.0 / (1.0 + (0.5 + (0.25 * (2.0 - e))))          # right-nested: every level keeps operands waiting
+        t = state.x
+        for k in range(60):
+            t = (k + 1.0) - (t * 0.5)
+        acc = 1.0
+        for k in range(45):
+            acc = state.x + (state.x * (state.x - acc))
+        return ld.norm(state.x, 0, 1) + e + acc
+    s = _model_only(pkg, {"x": {"type": "real"}}, deep, None)
+    log = C.create_string_buffer(4096)
+    rc = pkg._ffi.lib().amwg_jit_compile_check(C.byref(s._model_keepalive[-1]), 1, log, len(log), None, 0)
+    # either the lowering keeps it shallow (fine) or validation names the limit; never silently accepted beyond the stack
+    if rc == -1:
+        assert "operand stack" in log.value.decode()
+
+
+def test_parameter_array_indexed_out_of_bounds_is_refused(pkg):
+    """mu[data.g[i]] with 1-based group ids reads past the parameter; JS yields undefined -> NaN, here it must not
+    silently alias the next parameter."""
+    ld = pkg.ld
+    J = 3
+    g = np.repeat(np.arange(1, J + 1), 20).astype(float)           # 1..3: out of bounds for a length-3 array
+    y = np.random.default_rng(3).normal(0, 1, g.size)
+
+    def hier(state, d):
+        lp = ld.unif(state.sigma, 0, 10)
+        for j in range(J):
+            lp += ld.norm(state.mu[j], 0, 10)
+        for i in pkg.mcmc.points(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]], state.sigma)
+        return lp
+    P = {"mu": {"type": "real", "dim": [J]}, "sigma": {"type": "real", "lower": 0}}
+    with pytest.raises(pkg.JsThrow, match="outside its bounds"):
+        _model_only(pkg, P, hier, {"y": y, "g": g})
+    _model_only(pkg, P, hier, {"y": y, "g": g - 1})                 # 0-based ids are fine

@@ -32,7 +32,8 @@ def _oracle_logpost(orc, model, data, params, state):
 
 def test_normal_model_becomes_two_terms_and_a_plate(pkg, orc):
     prog, derived, n = _trace(pkg, models.norm_post_test(pkg.ld), models.PARAMS1, config2_data().tolist())
-    assert prog.summary == ["term LD_NORM", "term LD_UNIF", "plate NORM_IID n=1024"]
+    assert prog.summary[:3] == ["term LD_NORM", "term LD_UNIF", "plate NORM_IID n=1024"]
+    assert prog.summary[3].startswith("pre-evaluated statistics: 1 plate(s), 1024 points") and prog.stat_prog >= 0
     assert derived == ["var"] and n == 2
     assert len(prog.fold_prog) >= 3                    # log(2pi)-log(100), 2*100*100, log(1/(100-0)) are computed once
     consts = prog_eval.fold_constants(prog, orc.lib())
@@ -221,13 +222,13 @@ def test_pre_evaluated_statistics_programs(pkg, orc, monkeypatch):
                 st[c] = props[c]
                 for k in range(prog.touch_off[c], prog.touch_off[c + 1]):
                     cache[prog.touch_terms[k]] = cand[prog.touch_terms[k]]
-    # config-2 shape: both parameters scalar, the plate's mean is mu. Eligible, but with two components it does not pay (measured):
-    # only lowered this way on request
+    # config-2 shape: both parameters scalar, the plate's mean is mu: lowered the same way (the run-time specialised sweep makes
+    # one data pass per sweep pay for two-component models too); AMWG_STAT_LOWERING=0 keeps the full program
+    monkeypatch.setenv("AMWG_STAT_LOWERING", "0")
     prog, _, _ = _trace(pkg, models.norm_post_readme(ld), models.PARAMS1, config2_data().tolist())
     assert prog.stat_prog == -1 and prog.n_terms == 0
-    monkeypatch.setenv("AMWG_STAT_LOWERING", "2")
-    prog, _, _ = _trace(pkg, models.norm_post_readme(ld), models.PARAMS1, config2_data().tolist())
     monkeypatch.delenv("AMWG_STAT_LOWERING")
+    prog, _, _ = _trace(pkg, models.norm_post_readme(ld), models.PARAMS1, config2_data().tolist())
     assert prog.stat_prog >= 0 and prog.n_sum_terms == 3 and prog.n_terms == 4
     assert list(prog.touch_terms[prog.touch_off[0]:prog.touch_off[1]]) == [0, 3, 2] and list(prog.touch_terms[prog.touch_off[1]:prog.touch_off[2]]) == [1, 2]
     # a mean that reads two components cannot be pre-evaluated; neither can a model with a binary parameter; `faithful` keeps the JS loop
