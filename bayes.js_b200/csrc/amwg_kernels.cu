@@ -74,6 +74,7 @@ struct ModelDev {
   const unsigned char* adapting;   // [D] global, host-maintained (start/stop_adaptation)
   int phase_sync;                  // 1: every chain takes the same number of steps per sweep -> CTA-wide phase barriers are legal
   int ring_smem_off;               // byte offset of the 2-stage TMA tile ring in dynamic smem, -1: every column is resident
+  int has_pois;                    // the model has a POIS_LOGLIN plate: stage_model fills ctx.exp_tab
   int n_variant_comps;             // binary components whose value selects the program (amwg_model.variant_*), 0 = single program
   int variant_comps[AMWG_MAX_VARIANT_COMPS];
   int variant_logpost[1 << AMWG_MAX_VARIANT_COMPS];
@@ -95,6 +96,7 @@ struct Ctx {                       // lives in shared memory
   unsigned ring_saddr;             // shared address of the TMA tile ring (0: none, or this kernel does not run CTA-uniformly)
   unsigned ring_uses[kRingStages]; // fills of each stage so far (mbarrier phase parity = fills & 1)
   unsigned long long ring_bar[kRingStages];
+  double exp_tab[256];             // 2^(j/256) for the Poisson plate's exponential (filled only when the model has such a plate)
 };
 
 struct EvalStateBase {
@@ -167,6 +169,7 @@ __device__ __forceinline__ void stage_model(const ModelDev& m, unsigned char* sm
     }
     ctx.norm_c0 = -0.5 * js_log(2 * AMWG_JS_PI);
   }
+  if (m.has_pois) for (int j = threadIdx.x; j < 256; j += blockDim.x) ctx.exp_tab[j] = exp2((double)j * (1.0 / 256.0));
   __syncthreads();
   mbar_wait(bar, 0);
 }
@@ -261,62 +264,128 @@ __device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const E
   return norm_factorised(ctx, (double)pl.n, S, sd);
 }
 
-// sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop), using log(exp(eta)) -> eta
-// and the precomputed lfactorial(y_i) column:  y*eta - exp(eta) - lfact.  (KS-level parity; real parameters only.)
-// Rows are consumed from shared memory: resident columns directly, larger ones through the TMA tile ring
-// (stage layout: X rows | y | lfactorial, three bulk copies per stage on one mbarrier).
-__device__ __forceinline__ void pois_rows(const double* __restrict__ X, const double* __restrict__ y, const double* __restrict__ lf,
-                                          int rows, int K, const double* beta, double& s0, double& s1) {
-  for (int i = 0; i < rows; ++i) {
-    double eta = 0.0;
-    const double* xr = X + (size_t)i * K;
-    for (int k = 0; k < K; ++k) eta = fma(xr[k], beta[k], eta);
-    double t = fma(y[i], eta, -exp(eta)) - lf[i];
-    if (i & 1) s1 += t; else s0 += t;
+// sum_i ld.pois(y_i, exp(eta_i)), eta_i = sum_k X_ik beta_k (k ascending, as the JS loop). With log(exp(eta)) -> eta the sum is
+//     sum_i y_i eta_i  -  sum_i exp(eta_i)  -  sum_i lfactorial(y_i)
+// whose first part is linear in beta, beta . (X^T y), and whose last part is a constant: the host precomputes X^T y and the
+// lfactorial total (plate column [2], amwg.h), and the O(N) work per evaluation is the dot product and the exponential of every
+// row -- the part that depends on beta non-linearly. (KS-level parity; real parameters only; `faithful` handles use the JS loop.)
+// Rows are consumed from shared memory: a resident X directly, a larger one through the TMA tile ring.
+//
+// exp(): table-driven, 2^(j/256) (256 entries in shared memory, filled once per CTA) times a degree-4 polynomial on
+// |r| <= ln2/512 (truncation 4e-17 relative): 9 fp64-pipe instructions including the accumulation, against ~25 for exp().
+__device__ __forceinline__ double exp_acc(double x, unsigned tab_sa, double s) {       // s + exp(x)
+  if (!(fabs(x) < 690.0)) return s + exp(x);                      // huge, infinite or NaN arguments: the library function
+  const double tm = fma(x, 369.3299304675746, 6755399441055744.0);      // x * 256/ln2 + 1.5*2^52: the integer lands in the low word
+  const int ki = __double2loint(tm);
+  const double kf = tm - 6755399441055744.0;
+  double r = fma(kf, -0.0027076061742263846, x);                   // Cody-Waite: ln2/256 = HI (32 bits) + LO
+  r = fma(kf, 1.6409824502660487e-13, r);
+  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  p = fma(p, r, 0.5);
+  p = fma(p, r, 1.0);
+  p = fma(p, r, 1.0);
+  const double T = lds_f64_sa(tab_sa + 8u * (unsigned)(ki & 255));
+  const double Ts = __hiloint2double(__double2hiint(T) + ((ki >> 8) << 20), __double2loint(T));      // * 2^(ki >> 8)
+  return fma(Ts, p, s);
+}
+
+template <int K>
+__device__ __forceinline__ void pois_rows(unsigned xsa, int rows, const double (&beta)[K], unsigned tab_sa, double& s0, double& s1) {
+  // two rows per iteration: two independent dependency chains per thread
+  int i = 0;
+  for (; i + 2 <= rows; i += 2, xsa += 16u * K) {
+    double e0 = 0.0, e1 = 0.0;
+    if constexpr ((K & 1) == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k += 2) {
+        const double2 a = lds_f64x2(xsa + 8u * k), b = lds_f64x2(xsa + 8u * (K + k));
+        e0 = fma(a.x, beta[k], e0); e1 = fma(b.x, beta[k], e1);
+        e0 = fma(a.y, beta[k + 1], e0); e1 = fma(b.y, beta[k + 1], e1);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; ++k) { e0 = fma(lds_f64_sa(xsa + 8u * k), beta[k], e0); e1 = fma(lds_f64_sa(xsa + 8u * (K + k)), beta[k], e1); }
+    }
+    s0 = exp_acc(e0, tab_sa, s0);
+    s1 = exp_acc(e1, tab_sa, s1);
   }
+  if (i < rows) {
+    double e0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) e0 = fma(lds_f64_sa(xsa + 8u * k), beta[k], e0);
+    s0 = exp_acc(e0, tab_sa, s0);
+  }
+}
+
+// rows from global / L2 when neither residency nor the ring applies (models whose chains take different steps per sweep)
+template <int K>
+__device__ __forceinline__ void pois_rows_global(const double* __restrict__ X, int rows, const double (&beta)[K], unsigned tab_sa, double& s0, double& s1) {
+  for (int i = 0; i < rows; ++i) {
+    double e = 0.0;
+#pragma unroll
+    for (int k = 0; k < K; ++k) e = fma(X[(size_t)i * K + k], beta[k], e);
+    if (i & 1) s1 = exp_acc(e, tab_sa, s1); else s0 = exp_acc(e, tab_sa, s0);
+  }
+}
+
+template <int K>
+__device__ __forceinline__ double pois_plate_k(Ctx& ctx, const amwg_plate& pl, const EvalStateBase& es) {
+  const double* __restrict__ X = ctx.col[pl.col[1]];
+  const double* __restrict__ stats = ctx.col[pl.col[2]];          // [X^T y (K) | sum lfactorial(y)]
+  const int base = pl.iparam[0], n = pl.n;
+  double beta[K];
+  double lin = 0.0;
+#pragma unroll
+  for (int k = 0; k < K; ++k) { beta[k] = es.comp(base + k); lin = fma(stats[k], beta[k], lin); }
+  const unsigned tab_sa = smem_u32(ctx.exp_tab);
+  double s0 = 0.0, s1 = 0.0;
+  const unsigned xres = ctx.col_saddr[pl.col[1]];
+  if (xres) {
+    pois_rows<K>(xres, n, beta, tab_sa, s0, s1);
+  } else if (!ctx.ring_saddr || (reinterpret_cast<unsigned long long>(X) & 15ull)) {
+    pois_rows_global<K>(X, n, beta, tab_sa, s0, s1);
+  } else {
+    const int R = (int)((kRingStageBytes / (unsigned)(K * 8)) & ~1u);          // rows per stage (even: every tile is a multiple of 16 B)
+    const int ntiles = (n + R - 1) / R;
+    __syncthreads();
+    const unsigned u0 = ctx.ring_uses[0], u1 = ctx.ring_uses[1];
+    if (threadIdx.x == 0)
+      for (int t = 0; t < 2 && t < ntiles; ++t) {
+        const int rows = min(R, n - t * R);
+        ring_issue(ctx, t, X + (size_t)t * R * K, (unsigned)((rows * K * 8 + 15) & ~15));
+      }
+    for (int t = 0; t < ntiles; ++t) {
+      const int st = t & 1;
+      mbar_wait(&ctx.ring_bar[st], ((st ? u1 : u0) + (unsigned)(t >> 1)) & 1u);
+      pois_rows<K>(ctx.ring_saddr + (unsigned)st * kRingStageBytes, min(R, n - t * R), beta, tab_sa, s0, s1);
+      __syncthreads();
+      if (threadIdx.x == 0 && t + 2 < ntiles) {
+        const int rows = min(R, n - (t + 2) * R);
+        ring_issue(ctx, st, X + (size_t)(t + 2) * R * K, (unsigned)((rows * K * 8 + 15) & ~15));
+      }
+    }
+    if (threadIdx.x == 0) { ctx.ring_uses[0] = u0 + (unsigned)((ntiles + 1) >> 1); ctx.ring_uses[1] = u1 + (unsigned)(ntiles >> 1); }
+  }
+  return (lin - (s0 + s1)) - stats[K];
 }
 
 __device__ __noinline__ double plate_pois_loglin(const Ctx& ctx_in, int q, const EvalStateBase& es) {
   Ctx& ctx = const_cast<Ctx&>(ctx_in);
   const amwg_plate& pl = ctx.plates[q];
-  const double* __restrict__ y = ctx.col[pl.col[0]] + pl.iparam[2];
-  const double* __restrict__ X = ctx.col[pl.col[1]];
-  const double* __restrict__ lf = ctx.col[pl.col[2]];
-  const int K = pl.iparam[1], base = pl.iparam[0], n = pl.n;
-  double beta[16];
-  for (int k = 0; k < K && k < 16; ++k) beta[k] = es.comp(base + k);
-  double s0 = 0.0, s1 = 0.0;
-  const bool resident = ctx.col_saddr[pl.col[0]] && ctx.col_saddr[pl.col[1]] && ctx.col_saddr[pl.col[2]];
-  const bool aligned = ((reinterpret_cast<unsigned long long>(y) | reinterpret_cast<unsigned long long>(X) | reinterpret_cast<unsigned long long>(lf)) & 15ull) == 0;
-  if (resident || !ctx.ring_saddr || !aligned) {
-    pois_rows(X, y, lf, n, K, beta, s0, s1);           // shared memory (generic addressing) or, without the ring, L2
-    return s0 + s1;
+  switch (pl.iparam[1]) {                                          // the coefficients live in registers: one instance per K
+    case 1: return pois_plate_k<1>(ctx, pl, es);
+    case 2: return pois_plate_k<2>(ctx, pl, es);
+    case 3: return pois_plate_k<3>(ctx, pl, es);
+    case 4: return pois_plate_k<4>(ctx, pl, es);
+    case 5: return pois_plate_k<5>(ctx, pl, es);
+    case 6: return pois_plate_k<6>(ctx, pl, es);
+    case 7: return pois_plate_k<7>(ctx, pl, es);
+    case 8: return pois_plate_k<8>(ctx, pl, es);
+    case 10: return pois_plate_k<10>(ctx, pl, es);
+    case 12: return pois_plate_k<12>(ctx, pl, es);
+    case 16: return pois_plate_k<16>(ctx, pl, es);
+    default: return CUDART_NAN;                                    // the host only emits the plate for these K (tracer._loglinear)
   }
-  const int R = (int)((kRingStageBytes / (unsigned)((K + 2) * 8)) & ~1u);        // rows per stage (even: every piece is a multiple of 16 B)
-  const int ntiles = (n + R - 1) / R;
-  __syncthreads();
-  const unsigned u0 = ctx.ring_uses[0], u1 = ctx.ring_uses[1];
-  auto issue = [&](int t, int stage) {
-    const int r0 = t * R, rows = min(R, n - r0);
-    const unsigned bx = (unsigned)((rows * K * 8 + 15) & ~15), by = (unsigned)((rows * 8 + 15) & ~15);
-    const unsigned dst = ctx.ring_saddr + (unsigned)stage * kRingStageBytes, barsa = smem_u32(&ctx.ring_bar[stage]);
-    mbar_expect_tx(&ctx.ring_bar[stage], bx + 2u * by);
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(X + (size_t)r0 * K), "r"(bx), "r"(barsa) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (unsigned)(R * K * 8)), "l"(y + r0), "r"(by), "r"(barsa) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + (unsigned)(R * (K + 1) * 8)), "l"(lf + r0), "r"(by), "r"(barsa) : "memory");
-  };
-  if (threadIdx.x == 0) for (int t = 0; t < 2 && t < ntiles; ++t) issue(t, t);
-  for (int t = 0; t < ntiles; ++t) {
-    const int st = t & 1;
-    mbar_wait(&ctx.ring_bar[st], ((st ? u1 : u0) + (unsigned)(t >> 1)) & 1u);
-    const int rows = min(R, n - t * R);
-    const double* sp = reinterpret_cast<const double*>(__cvta_shared_to_generic((size_t)(ctx.ring_saddr + (unsigned)st * kRingStageBytes)));
-    pois_rows(sp, sp + (size_t)R * K, sp + (size_t)R * (K + 1), rows, K, beta, s0, s1);
-    __syncthreads();
-    if (threadIdx.x == 0 && t + 2 < ntiles) issue(t + 2, st);
-  }
-  if (threadIdx.x == 0) { ctx.ring_uses[0] = u0 + (unsigned)((ntiles + 1) >> 1); ctx.ring_uses[1] = u1 + (unsigned)(ntiles >> 1); }
-  return s0 + s1;
 }
 
 // ---- the interpreter: ONE instance of the opcode switch in the whole library ---------------------------------------------
@@ -1359,6 +1428,8 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
   m.n_columns = md->n_columns; m.n_plates = md->n_plates; m.n_params = md->n_params; m.D = md->n_comp;
   m.n_derived = md->n_derived; m.logpost_prog = md->logpost_prog; m.derived_prog = md->derived_prog;
   m.n_variant_comps = md->n_variant_comps;
+  m.has_pois = 0;
+  for (int q = 0; q < md->n_plates; ++q) m.has_pois |= md->plates[q].kind == AMWG_PLATE_POIS_LOGLIN;
   for (int k = 0; k < md->n_variant_comps; ++k) m.variant_comps[k] = md->variant_comps[k];
   for (int v = 0; v < (md->n_variant_comps ? (1 << md->n_variant_comps) : 0); ++v) {
     m.variant_logpost[v] = md->variant_logpost[v];

@@ -60,6 +60,8 @@ __device__ __forceinline__ double2 lds_f64x2(unsigned saddr) {
   return v;
 }
 
+__device__ __forceinline__ double lds_f64_sa(unsigned saddr) { double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr)); return v; }
+
 // ---- plates: the O(N) likelihood sums -----------------------------------------------------------------------------
 // sum_i (x_i - mean)^2 : 2 fp64-pipe instructions per point (DADD + DFMA), AMWG_NACC independent accumulators, eight points
 // per block read as four 16-byte warp-broadcast loads (ld.shared.v2.f64 when `saddr` != 0, i.e. the column sits in shared

@@ -69,13 +69,32 @@ def _sym_or_num(x):
     return x if is_sym(x) else lift(x)
 
 
+def _concrete(tree):
+    """A composed ld.* called with plain numbers outside log_post: evaluate its expression on the device, one primitive at a time
+    (same opcodes, same arithmetic as inside a program), and hand back a float like the other ld.* do."""
+    if _tracer._ACTIVE:
+        return tree
+    stack = [tree]
+    while stack:
+        n = stack.pop()
+        if n.op in ("COMP", "DATA", "DATA_I", "COMP_I"):
+            return tree                                  # symbolic somewhere: stays a recorded expression
+        stack.extend(n.args)
+
+    def ev(n):
+        if n.op == "CONST":
+            return float(n.val)
+        return _device_eval(n.op, [ev(a) for a in n.args])
+    return ev(tree)
+
+
 def bivarnorm(x, mean, sd, corr):
     """distributions.js:125-133 -- composed from device primitives in the JS operation order."""
     x0, x1, m0, m1, s0, s1, r = map(_sym_or_num, (x[0], x[1], mean[0], mean[1], sd[0], sd[1], corr))
     z = Math.pow(x0 - m0, 2) / Math.pow(s0, 2) + Math.pow(x1 - m1, 2) / Math.pow(s1, 2) - \
         (2 * r * (x0 - m0) * (x1 - m1)) / (s0 * s1)
     nf = -(Math.log(2) + Math.log(Math.PI) + Math.log(s0) + Math.log(s1) + 0.5 * Math.log(1 - Math.pow(r, 2)))
-    return nf - z / (2 * (1 - Math.pow(r, 2)))
+    return _concrete(nf - z / (2 * (1 - Math.pow(r, 2))))
 
 
 def dirichlet(x, alpha):
@@ -88,7 +107,7 @@ def dirichlet(x, alpha):
         sum_alpha = sum_alpha + a
         sum_lgamma_alpha = sum_lgamma_alpha + Sym("LGAMMA", (a,))
         s = s + (a - 1) * Math.log(x[i])
-    return Sym("LGAMMA", (sum_alpha,)) - sum_lgamma_alpha + s
+    return _concrete(Sym("LGAMMA", (sum_alpha,)) - sum_lgamma_alpha + s)
 
 
 def cat(x, probs):
@@ -98,4 +117,4 @@ def cat(x, probs):
     picked = lift(float("nan"))
     for k in range(n, 0, -1):
         picked = where(xs == k, Math.log(probs[k - 1]), picked)
-    return where(Sym("OR", (xs < 1, xs > n)), -float("inf"), picked)
+    return _concrete(where(Sym("OR", (xs < 1, xs > n)), -float("inf"), picked))

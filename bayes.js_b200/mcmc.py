@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _ffi
 from ._ffi import AmwgColumn, AmwgCompOptions, AmwgModel, AmwgParam, AmwgPlate, BINARY, INT, REAL
-from .tracer import JsThrow, Math, points, trace, where  # noqa: F401  (re-exported)
+from .tracer import JsThrow, Math, Sym, points, trace, where  # noqa: F401  (re-exported)
 
 Infinity = float("inf")
 _TYPE_CODE = {"real": REAL, "int": INT, "binary": BINARY}
@@ -209,6 +209,20 @@ class _HostStream:
         return float(cls._block[k])
 
 
+def set_random_stream(seed: int, chain: int = 0, position: int = 0):
+    """Not in the reference (its helpers use the engine's unseedable Math.random): choose the Philox stream (seed, chain) the
+    exported helpers runif / runif_discrete / rnorm draw from, and the position in it."""
+    _HostStream.seed, _HostStream.chain, _HostStream.n = int(seed) & 0xFFFFFFFFFFFFFFFF, int(chain) & 0xFFFFFFFFFFFFFFFF, int(position)
+    _HostStream._block, _HostStream._block0 = np.empty(0), 0
+
+
+def _device_log(x: float) -> float:
+    """Math.log as the device computes it (fdlibm e_log, csrc/amwg_math.cuh): the helpers agree with the sampler bit for bit."""
+    a, out = np.array([float(x)]), np.empty(1)
+    _ffi.check(_ffi.lib().amwg_primitive_eval(0, a.ctypes.data, 1, 0, 0, out.ctypes.data, _default_device()))
+    return float(out[0])
+
+
 def runif(min, max):
     """mcmc.js:31-33"""
     return _HostStream.random() * (max - min) + min
@@ -227,7 +241,7 @@ def rnorm(mean, sd):
         x = u - 0.449871
         y = abs(v) + 0.386595
         q = x * x + y * (0.19600 * y - 0.25472 * x)
-        if not (q > 0.27597 and (q > 0.27846 or v * v > -4 * math.log(u) * u * u)):
+        if not (q > 0.27597 and (q > 0.27846 or v * v > -4 * _device_log(u) * u * u)):
             break
     return (v / u) * sd + mean
 
@@ -502,7 +516,10 @@ class AmwgSampler(Sampler):
             spans[name] = (len(entries), len(e))
             entries.extend(e)
         n = int(n_iterations)
-        thin = int(self.thinning_interval)
+        thin = abs(int(self.thinning_interval))                 # `i % thin === 0` (mcmc.js:1021): the sign of thin does not matter ...
+        if thin == 0:                                           # ... and i % 0 is NaN: nothing is ever recorded, the chains still step
+            self.burn(max(n, 0))
+            return {name: np.empty((0,)) for name in monitored}
         rows = 0 if n <= 0 else (n + thin - 1) // thin
         raw = self._sample_raw(n, thin, entries, rows)          # [rows, n_entries, chains]
         out = {}
@@ -543,8 +560,8 @@ class AmwgSampler(Sampler):
             spans[name] = (len(entries), len(e))
             entries.extend(e)
         n = int(n_iterations)
-        thin = int(self.thinning_interval)
-        rows = 0 if n <= 0 else (n + thin - 1) // thin
+        thin = abs(int(self.thinning_interval))
+        rows = 0 if (n <= 0 or thin == 0) else (n + thin - 1) // thin
         if rows == 0 or not entries:
             raise JsThrow("sample_summary needs at least one kept iteration and one monitored entry")
         L = _ffi.lib()
@@ -630,7 +647,7 @@ class AmwgSampler(Sampler):
         return float(_ffi.lib().amwg_last_sweep_kernel_ms(self._handle))
 
     def program_summary(self) -> List[str]:
-        return list(self._program.summary) + [self.jit_status()[1]]
+        return list(self._program.summary)
 
     def jit_status(self):
         """(active, note): does this handle step with a kernel specialised for its model at run time (csrc/amwg_jit.cuh)?"""
@@ -721,15 +738,39 @@ class _SteppedModel(AmwgSampler):
         self._user_state, self._zero_arg_log_post, self._direct = state, log_post, direct_options
         names = list(params.keys())
 
+        def foreign(v, key):
+            """numeric entries of `state` that belong to OTHER steppers: marked, so that a log_post that reads them is noticed"""
+            if is_number(v):
+                return Sym("FOREIGN", (), key)
+            if isinstance(v, list):
+                return [foreign(x, key) for x in v]
+            return v
+
         def recorded(sym_state, _data):
-            saved = {n: state[n] for n in names}
+            others = [k for k in list(state.keys()) if k not in names]
+            saved = {n: state[n] for n in names + others}
             try:
                 for n in names:
                     state[n] = sym_state[n]
-                return log_post()
+                for k in others:
+                    state[k] = foreign(saved[k], k)
+                result = log_post()
             finally:
-                for n in names:
+                for n in saved:
                     state[n] = saved[n]
+            # The reference's steppers close over the LIVE state object (mcmc.js:433-437): a second stepper's updates are seen by
+            # this one's log_post. Here log_post is recorded once, so a value owned by another stepper would be frozen into the
+            # device program -- refuse instead of silently sampling the wrong conditional.
+            stack, seen = [result] if isinstance(result, Sym) else [], 0
+            while stack:
+                node = stack.pop()
+                if node.op == "FOREIGN":
+                    raise JsThrow("log_post reads state." + str(node.val) + ", which this stepper does not step: composing several "
+                                  "stand-alone steppers over one state object is not supported on the device; give one "
+                                  "AmwgStepper / AmwgSampler all the parameters")
+                stack.extend(node.args)
+                seen += 1
+            return result
         p = copy.deepcopy(params)
         for n in names:
             p[n]["init"] = copy.deepcopy(state[n])          # a stepper starts from the state it is given, not from params.init

@@ -134,10 +134,15 @@ class _Math:
     def pow(x, y): return Sym("POW", (lift(x), lift(y)))
 
     @staticmethod
-    def max(a, b): return where(lift(a) > lift(b), a, b)
+    def max(a, b):
+        """Math.max: NaN if either argument is NaN (x != x), like the engine's"""
+        a, b = lift(a), lift(b)
+        return where(Sym("OR", (a != a, b != b)), float("nan"), where(a > b, a, b))
 
     @staticmethod
-    def min(a, b): return where(lift(a) < lift(b), a, b)
+    def min(a, b):
+        a, b = lift(a), lift(b)
+        return where(Sym("OR", (a != a, b != b)), float("nan"), where(a < b, a, b))
 
 
 Math = _Math()
@@ -724,10 +729,13 @@ class Lowering:
                 xcol, K, base = lin
                 y = body.args[0]
                 ycol = self.t.columns[y.val[0]][y.val[1]: y.val[1] + n]
-                lf = np.array([_lfactorial_host(v) for v in ycol])      # constant in the parameters
+                # sum_i [y_i eta_i - exp(eta_i) - lfactorial(y_i)]: the first part is beta . (X^T y), the last a constant; both are
+                # precomputed here (constant in the parameters), the device sums exp(eta_i) over the rows
+                X = self.t.columns[xcol][: n * K].reshape(n, K)
+                stats = np.concatenate([X.T @ ycol, [float(np.sum(_lfactorial_host_vec(ycol)))]])
                 pl.update(kind=PLATE_POIS_LOGLIN)
                 pl["col"][0] = y.val[0]; pl["iparam"][2] = y.val[1]
-                pl["col"][1] = xcol; pl["col"][2] = self.t.add_column(lf)
+                pl["col"][1] = xcol; pl["col"][2] = self.t.add_column(stats)
                 pl["iparam"][0] = base; pl["iparam"][1] = K
                 p.summary.append(f"plate POIS_LOGLIN n={n} K={K}")
         p.plates.append(pl)
@@ -799,7 +807,7 @@ class Lowering:
             c, off, stride, _pid = a.val
             if xcol is None: xcol, base = c, b.val
             if c != xcol or off != k or stride != len(terms) or b.val != base + k: return None
-        if xcol is None or len(terms) > 16: return None
+        if xcol is None or len(terms) not in POIS_LOGLIN_K: return None      # the device keeps the coefficients in registers: one kernel instance per K
         return xcol, len(terms), base
 
     # -- main -------------------------------------------------------------------------------------
@@ -1131,6 +1139,24 @@ def _lfactorial_host(y: float) -> float:
     return math.log(2.5066282746310005 * ser / xx) - tmp
 
 
+def _lfactorial_host_vec(y: np.ndarray) -> np.ndarray:
+    """_lfactorial_host over an array (the data column of a Poisson plate has up to millions of entries)."""
+    y = np.asarray(y, dtype=np.float64)
+    x = y + 1.0
+    cof = [76.18009172947146, -86.50532032941677, 24.01409824083091, -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5]
+    ser = np.full_like(x, 1.000000000190015)
+    yy = x.copy()
+    tmp = x + 5.5
+    with np.errstate(invalid="ignore", divide="ignore"):
+        tmp = tmp - (x + 0.5) * np.log(tmp)
+        for c in cof:
+            yy = yy + 1.0
+            ser = ser + c / yy
+        out = np.log(2.5066282746310005 * ser / x) - tmp
+    return np.where(y < 0, np.nan, out)
+
+
+POIS_LOGLIN_K = (1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 16)
 MAX_VARIANT_COMPS = 4
 
 

@@ -439,7 +439,7 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dt, dt_e2e, kernel_ms, dt_sum, dt_root, dt_all = [float(v) for v in times.tolist()]
-    info = sampler.program_summary()
+    info = sampler.program_summary() + ["sweep kernel: " + sampler.jit_status()[1]]
     sampler.close()
 
     if rank == 0:

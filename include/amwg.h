@@ -142,14 +142,16 @@ enum {
                                N*(-0.5*log(2pi) - log(sd)) - sum_i (x_i-mean)^2 / (2*sd*sd)     (KS-level parity)   */
   AMWG_PLATE_BERN_IID,      /* operand A = p.  sum_i ld.bern(y_i, p), sequential, bit-faithful                       */
   AMWG_PLATE_NORM_GROUPED,  /* operand A = sd.  sum_i ld.norm(y_i, mu[g_i], sd); points sorted by group              */
-  AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k))                                          */
+  AMWG_PLATE_POIS_LOGLIN    /* sum_i ld.pois(y_i, exp(sum_k X_ik * beta_k)) = beta . (X^T y) - sum_i exp(X_i . beta) - sum_i lfactorial(y_i):
+                               the linear part and the constant come precomputed (col[2]), the device sums the exponentials.
+                               K in {1..8, 10, 12, 16}                                           (KS-level parity)   */
 };
 
 typedef struct {
   int32_t kind;          /* AMWG_PLATE_*                                                          */
   int32_t n;             /* number of points                                                       */
   int32_t col[4];        /* data columns: [0] x or y; GROUPED: [1] group start offsets (J+1);
-                            POIS_LOGLIN: [1] X row-major n*K, [2] lfactorial(y) (filled by the host) */
+                            POIS_LOGLIN: [1] X row-major n*K, [2] K+1 values filled by the host: X^T y, then sum_i lfactorial(y_i) */
   int32_t iparam[4];     /* GROUPED: [0] first mu component, [1] J;  POIS_LOGLIN: [0] first beta component, [1] K;
                             all specialised kinds: [2] offset of the plate's first point inside col[0]              */
 } amwg_plate;

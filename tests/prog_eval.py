@@ -149,10 +149,10 @@ def run(prog, consts, state, pc, O, want_top=False, der=None, moved=-1, val=0.0,
             elif pl["kind"] == PLATE_POIS_LOGLIN:
                 base, K = pl["iparam"][0], pl["iparam"][1]
                 X = np.asarray(cols[pl["col"][1]]).reshape(-1, K)[:n]
-                lf = np.asarray(cols[pl["col"][2]])[:n]
+                stats = np.asarray(cols[pl["col"][2]])           # [X^T y (K) | sum lfactorial(y)], amwg.h
                 beta = np.array([comp(base + k) for k in range(K)])
                 eta = X @ beta
-                plate_v = float(np.sum(x * eta - np.exp(eta) - lf))
+                plate_v = float(stats[:K] @ beta - np.sum(np.exp(eta)) - stats[K])
                 lp = lp + plate_v
             else:
                 raise AssertionError("generic plates are LOOP_BEGIN/LOOP_END")

@@ -53,12 +53,53 @@ def test_gpu_reproduces_the_js_sampler_draw_for_draw(case, gpu_pkg):
 def test_gpu_ld_matches_the_js_bit_for_bit(gpu_pkg):
     ld = gpu_pkg.ld
     for fname, rows in G["ld"].items():
-        if fname in ("bivarnorm", "dirichlet", "cat", "t", "weibull"):
-            continue
+        if fname in ("bivarnorm", "dirichlet", "cat"):
+            continue                                   # array arguments: test_gpu_ld_array_functions_match_the_js
         args = np.array([[float.fromhex(a) for a in r[0]] for r in rows])
         want = np.array([float.fromhex(r[1]) for r in rows])
         got = getattr(ld, fname)(*[args[:, k] for k in range(args.shape[1])])
-        assert gu.same(got, want), fname
+        if fname in ("t", "weibull"):
+            # these two go through Math.pow with a non-integer exponent. pow is the one Math function that is NOT pinned across the
+            # three sides (the goldens used the host's libm pow, the device uses CUDA's, V8 its own fdlibm port; all faithfully
+            # rounded): equal to a few ulp of the result instead of bit for bit
+            ok = (got == want) | (np.isnan(got) & np.isnan(want)) | (np.abs(got - want) <= 8 * np.spacing(np.abs(want)))
+            assert ok.all(), (fname, args[~ok][:3], got[~ok][:3], want[~ok][:3])
+        else:
+            assert gu.same(got, want), fname
+
+
+def _js_args(v):
+    if isinstance(v, list):
+        return [_js_args(x) for x in v]
+    return float.fromhex(v) if isinstance(v, str) else float(v)
+
+
+def test_gpu_ld_array_functions_match_the_js(gpu_pkg):
+    """ld.bivarnorm / ld.dirichlet / ld.cat take array arguments (distributions.js:123-134, 203-215, 232-238): the golden rows
+    keep them nested."""
+    ld = gpu_pkg.ld
+    for fname in ("bivarnorm", "dirichlet", "cat"):
+        for r in G["ld"].get(fname, []):
+            args = _js_args(r[0])
+            want = float.fromhex(r[1])
+            got = getattr(ld, fname)(*args)
+            got = float(np.asarray(got).reshape(-1)[0])
+            assert got == want or (np.isnan(got) and np.isnan(want)) or abs(got - want) <= 8 * np.spacing(abs(want)), (fname, args, got, want)
+
+
+def test_exported_helpers_match_the_js(gpu_pkg):
+    """mcmc.rnorm / runif / runif_discrete (mcmc.js:31-54) of the PRODUCT on the golden stream: same values and the same number of
+    Math.random() calls as the reference's own helpers."""
+    mcmc = gpu_pkg.mcmc
+    h = G["helpers"]
+    mcmc.set_random_stream(h["seed"], h["chain"])
+    got = [mcmc.rnorm(10, 5) for _ in h["rnorm_10_5"]]
+    assert gu.same(got, [float.fromhex(v) for v in h["rnorm_10_5"]])
+    got = [mcmc.runif(2, 5) for _ in h["runif_2_5"]]
+    assert gu.same(got, [float.fromhex(v) for v in h["runif_2_5"]])
+    got = [mcmc.runif_discrete(1, 6) for _ in h["runif_discrete_1_6"]]
+    assert gu.same(np.asarray(got, dtype=np.float64), [float.fromhex(v) if isinstance(v, str) else float(v) for v in h["runif_discrete_1_6"]])
+    assert mcmc._HostStream.n == h["uniforms_consumed"]
 
 
 @pytest.mark.parametrize("case", [c for c in G["samplers"] if c["log_post"] in ("spike_bern", "complex_model_post")],

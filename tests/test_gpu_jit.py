@@ -53,7 +53,7 @@ def test_headline_model_matches_the_interpreter_and_the_exact_posterior(gpu_pkg,
     b.burn(800)
     d = b.sample(50)
     n, ybar, s2 = x.size, x.mean(), x.var(ddof=1)
-    assert abs(d["mu"].mean() - ybar) < 0.02 and abs(d["mu"].std() - np.sqrt(s2 / n) * np.sqrt((n - 1) / (n - 3))) < 0.02
+    assert abs(d["mu"].mean() - ybar) < 0.02 and abs(d["mu"].std() - np.sqrt(s2 / n) * np.sqrt((n - 1) / (n - 4))) < 0.02
     # sigma has a flat prior on sigma: sigma^2 | y ~ Inv-chi2(n - 2, .): E[sigma] ~ s * sqrt((n-1)/2) * Gamma((n-3)/2) / Gamma((n-2)/2)
     from math import lgamma, exp, sqrt
     e_sigma = sqrt(s2) * sqrt((n - 1) / 2.0) * exp(lgamma((n - 3) / 2.0) - lgamma((n - 2) / 2.0))
