@@ -178,8 +178,15 @@ _KEYWORDS = {"var", "function", "return", "if", "else", "for", "while", "do", "b
              "default", "void"}
 
 
+class TokenList(list):
+    """tokens as (kind, value) pairs; `spans[i]` is the (start, end) of token i in `src` (Function.prototype.toString)"""
+    src = ""
+    spans: list = []
+
+
 def tokenize(src: str):
-    toks = []
+    toks = TokenList()
+    toks.src, toks.spans = src, []
     pos = 0
     while pos < len(src):
         m = _TOKEN.match(src, pos)
@@ -188,6 +195,7 @@ def tokenize(src: str):
         pos = m.end()
         if m.lastgroup == "ws":
             continue
+        toks.spans.append((m.start(), m.end()))
         kind, text = m.lastgroup, m.group(m.lastgroup)
         if kind == "num":
             toks.append(("num", float(int(text, 16)) if text[:2] in ("0x", "0X") else float(text)))
@@ -200,6 +208,7 @@ def tokenize(src: str):
         else:
             toks.append(("op", text))
     toks.append(("eof", None))
+    toks.spans.append((len(src), len(src)))
     return toks
 
 
@@ -213,6 +222,13 @@ _BINPREC = {"||": 1, "&&": 2, "|": 3, "^": 4, "&": 5, "==": 6, "!=": 6, "===": 6
 class Parser:
     def __init__(self, toks):
         self.t, self.i = toks, 0
+
+    def _text(self, start_tok):
+        """source text of tokens [start_tok, self.i)"""
+        spans = getattr(self.t, "spans", None)
+        if not spans:
+            return None
+        return self.t.src[spans[start_tok][0]:spans[self.i - 1][1]]
 
     def peek(self): return self.t[self.i]
     def next(self):
@@ -258,8 +274,9 @@ class Parser:
             if v == "function" and self.t[self.i + 1][0] == "id":
                 self.next()
                 name = self.next()[1]
+                start = self.i - 2
                 params, body = self.func_rest()
-                return ("funcdecl", name, params, body)
+                return ("funcdecl", name, params, body, self._text(start))
             if v == "return":
                 self.next()
                 e = None
@@ -484,9 +501,10 @@ class Parser:
             if v == "true": return ("bool", True)
             if v == "false": return ("bool", False)
             if v == "function":
+                start = self.i - 1
                 name = self.next()[1] if self.at("id") else ""
                 params, body = self.func_rest()
-                return ("func", name, params, body)
+                return ("func", name, params, body, self._text(start))
         if k == "op":
             if v == "(":
                 e = self.expression()
@@ -583,7 +601,7 @@ class Interpreter:
         if v is None: return "null"
         if isinstance(v, JSArray):
             return ",".join("" if (x is undefined or x is None) else self.to_str(x) for x in v.items)
-        if isinstance(v, JSFunction): return "function " + v.name + "() { [code] }"
+        if isinstance(v, JSFunction): return getattr(v, "source", None) or ("function " + v.name + "() { [native code] }")
         return "[object Object]"
 
     def to_key(self, v) -> str:
@@ -709,7 +727,77 @@ class Interpreter:
             return self.new_array(a)
         Array = make_ctor("Array", array_ctor, ap)
         Array.put("isArray", nat("isArray", lambda this, a: isinstance(a[0], JSArray) if a else False))
-        make_ctor("Function", lambda this, a: undefined, fp)
+        def function_ctor(this, a):
+            """new Function(p1, ..., pn, body): the body runs in the GLOBAL scope, like the real constructor"""
+            parts = [self.to_str(x) for x in a]
+            params, body = parts[:-1], (parts[-1] if parts else "")
+            src = "(function anonymous(" + ",".join(params) + "\n) {\n" + body + "\n})"
+            ast = Parser(tokenize(src)).expression()
+            return self.eval(ast, self.global_env)
+        make_ctor("Function", function_ctor, fp)
+        fp.put("toString", nat("toString", lambda this, a: self.to_str(this)))
+        sp = self.string_proto
+
+        def _s(this): return this if isinstance(this, str) else self.to_str(this)
+
+        def _i(a, k, default):
+            if len(a) <= k or a[k] is undefined: return default
+            v = self.to_num(a[k])
+            return default if v != v else int(v)
+        sp.put("charAt", nat("charAt", lambda this, a: (_s(this)[_i(a, 0, 0)] if 0 <= _i(a, 0, 0) < len(_s(this)) else "")))
+        sp.put("charCodeAt", nat("charCodeAt", lambda this, a: (float(ord(_s(this)[_i(a, 0, 0)])) if 0 <= _i(a, 0, 0) < len(_s(this)) else math.nan)))
+
+        def str_substring(this, a):
+            st = _s(this)
+            b, e = max(0, min(len(st), _i(a, 0, 0))), max(0, min(len(st), _i(a, 1, len(st))))
+            if b > e: b, e = e, b
+            return st[b:e]
+
+        def str_slice(this, a):
+            st = _s(this)
+            n = len(st)
+            b, e = _i(a, 0, 0), _i(a, 1, n)
+            if b < 0: b = max(0, n + b)
+            if e < 0: e = max(0, n + e)
+            return st[min(b, n):min(e, n)] if b < e else ""
+        sp.put("substring", nat("substring", str_substring))
+        sp.put("slice", nat("slice", str_slice))
+        sp.put("indexOf", nat("indexOf", lambda this, a: float(_s(this).find(self.to_str(a[0]) if a else "undefined", _i(a, 1, 0)))))
+        sp.put("toString", nat("toString", lambda this, a: _s(this)))
+        sp.put("split", nat("split", lambda this, a: self.new_array(list(_s(this)) if (a and a[0] == "") else _s(this).split(self.to_str(a[0])) if a else [_s(this)])))
+        sp.put("replace", nat("replace", lambda this, a: _s(this).replace(self.to_str(a[0]), self.to_str(a[1]), 1)))
+        sp.put("toLowerCase", nat("toLowerCase", lambda this, a: _s(this).lower()))
+        self.number_proto.put("toString", nat("toString", lambda this, a: self.to_str(this)))
+        self.number_proto.put("toFixed", nat("toFixed", lambda this, a: format(self.to_num(this), "." + str(int(self.to_num(a[0])) if a else 0) + "f")))
+
+        def arr_pop(this, a):
+            return this.items.pop() if this.items else undefined
+
+        def arr_shift(this, a):
+            return this.items.pop(0) if this.items else undefined
+
+        def arr_sort(this, a):
+            import functools
+            if a and isinstance(a[0], JSFunction):
+                this.items.sort(key=functools.cmp_to_key(lambda x, y: (lambda r: -1 if r < 0 else (1 if r > 0 else 0))(self.to_num(a[0].call(undefined, [x, y])))))
+            else:
+                this.items.sort(key=lambda x: self.to_str(x))
+            return this
+
+        def arr_reverse(this, a):
+            this.items.reverse()
+            return this
+        def arr_splice(this, a):
+            n = len(this.items)
+            start = int(self.to_num(a[0])) if a else 0
+            if start < 0: start = max(0, n + start)
+            start = min(start, n)
+            count = n - start if len(a) < 2 else max(0, min(int(self.to_num(a[1])), n - start))
+            removed = this.items[start:start + count]
+            this.items[start:start + count] = list(a[2:])
+            return self.new_array(removed)
+        ap.put("splice", nat("splice", arr_splice))
+        ap.put("pop", nat("pop", arr_pop)); ap.put("shift", nat("shift", arr_shift)); ap.put("sort", nat("sort", arr_sort)); ap.put("reverse", nat("reverse", arr_reverse))
         make_ctor("Number", lambda this, a: self.to_num(a[0]) if a else 0.0, self.number_proto)
         make_ctor("String", lambda this, a: self.to_str(a[0]) if a else "", self.string_proto)
         make_ctor("Date", lambda this, a: self.new_object(), JSObject(op))
@@ -752,6 +840,7 @@ class Interpreter:
         g["undefined"] = undefined
         g["isNaN"] = nat("isNaN", lambda this, a: self.to_num(a[0]) != self.to_num(a[0]))
         g["parseFloat"] = nat("parseFloat", lambda this, a: self.to_num(a[0]))
+        g["isFinite"] = nat("isFinite", lambda this, a: math.isfinite(self.to_num(a[0])))
 
     # -- running ----------------------------------------------------------------------------------------------------
     def run(self, src: str, this=None):
@@ -781,7 +870,7 @@ class Interpreter:
             for name, _ in s[1]:
                 env.vars.setdefault(name, undefined)
         elif k == "funcdecl":
-            env.vars[s[1]] = self.make_function(s[1], s[2], s[3], env)
+            env.vars[s[1]] = self.make_function(s[1], s[2], s[3], env, s[4] if len(s) > 4 else None)
         elif k == "block":
             self._hoist(s[1], env)
         elif k == "if":
@@ -800,8 +889,9 @@ class Interpreter:
             for _, body in s[2]:
                 self._hoist(body, env)
 
-    def make_function(self, name, params, body, env) -> JSFunction:
+    def make_function(self, name, params, body, env, source=None) -> JSFunction:
         f = JSFunction(self, params, body, env, name=name, proto=self.function_proto)
+        f.source = source
         proto = JSObject(self.object_proto)
         proto.put("constructor", f)
         f.put("prototype", proto)
@@ -969,7 +1059,7 @@ class Interpreter:
             r = f.call(obj, args)
             return r if isinstance(r, JSObject) else obj
         if k == "func":
-            return self.make_function(e[1], e[2], e[3], env)
+            return self.make_function(e[1], e[2], e[3], env, e[4] if len(e) > 4 else None)
         if k == "array":
             return self.new_array([self.eval(x, env) for x in e[1]])
         if k == "object":
