@@ -34,10 +34,10 @@
 
 namespace amwg {
 
-constexpr int kMaxColumns = 16;
+constexpr int kMaxColumns = 32;
 constexpr int kMaxParams = 16;       // substepper order is packed 4 bits per named parameter
 constexpr int kMaxDim0 = 256;        // top-level visit order of a multi-dim parameter (uint8 per entry)
-constexpr int kMaxDerived = 8;
+constexpr int kMaxDerived = 32;
 constexpr int kStack = 32;          // operand stack of the interpreter; validate_model rejects programs that need more
 #ifndef AMWG_THREADS
 #define AMWG_THREADS 128
@@ -1172,8 +1172,8 @@ static int validate_model(const amwg_model* md) {
   if (!md) return fail("amwg_create: model is NULL");
   if (md->abi_version != AMWG_ABI_VERSION) return fail("amwg_create: ABI version mismatch");
   if (md->n_params < 1 || md->n_params > kMaxParams) return fail("amwg_create: between 1 and 16 named parameters are supported");
-  if (md->n_columns > kMaxColumns) return fail("amwg_create: at most 16 data columns are supported");
-  if (md->n_derived > kMaxDerived) return fail("amwg_create: at most 8 derived quantities are supported");
+  if (md->n_columns > kMaxColumns) return fail("amwg_create: at most 32 data columns are supported");
+  if (md->n_derived > kMaxDerived) return fail("amwg_create: at most 32 derived quantities are supported");
   int D = 0;
   for (int p = 0; p < md->n_params; ++p) {
     const amwg_param& pa = md->params[p];

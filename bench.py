@@ -215,12 +215,6 @@ def cpu_port_draws_per_sec(orc, cfg: Config, seconds_target: float = 12.0):
     return n / t, f"1 chain x {n} draws of {cfg.workload.split(',')[0]}, single thread"
 
 
-def cpu_baseline_time(model, data, params, chains, burn, sample):
-    """cpu_baseline leg for scripts (like every use of oracle/ outside tests/ and smoke(), it lives in bench.py): seconds the CPU
-    restatement takes for `chains` x (burn + sample) draws, one thread."""
-    return graft.load_oracle().time_model(model, data, params, chains=chains, burn=burn, sample=sample)
-
-
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (Node is absent) on all host cores.
     One step = ONE C call that runs `cores` independent chains on `cores` pthreads (orc_run_chains_mt): no per-step Python."""

@@ -229,3 +229,21 @@ def test_complete_params_and_descriptor_match_the_reference_fixtures(host, pkg):
     assert co[0]["batch_size"] == 20 and co[0]["is_adapting"] == (1 if res["p1"]["is_adapting"][0] else 0) == 0
     assert co[0]["prop_log_scale"] == res["p1"]["prop_log_scale"][0] == 0
     assert [p["type"] for p in d["params"]] == [0, 1, 2] and d["init"] == [0.5, 1.0, 1.0]
+
+
+def test_napi_addon_is_well_formed_and_binds_every_export(pkg):
+    """js/amwg_napi.cc cannot be built here (no Node headers): it is syntax-checked against a stub of the Node-API declarations it
+    uses, and must bind every AMWG_API export of include/amwg.h."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I" + os.path.join(root, "tests", "napi_stub"), os.path.join(root, "js", "amwg_napi.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(root, "js", "amwg_napi.cc")).read()
+    hdr = open(os.path.join(root, "include", "amwg.h")).read()
+    exports = re.findall(r"AMWG_API\s+[\w\s\*]+?\b(amwg_\w+)\s*\(", hdr)
+    assert sorted(set(exports)) == sorted(pkg._ffi.EXPORTS)
+    for name in exports:
+        assert name + "(" in src, name + " has no binding in js/amwg_napi.cc"
