@@ -50,7 +50,7 @@ constexpr int kSyncThreads = AMWG_SYNC_THREADS;   // CTA size of the phase-synch
 constexpr int kAdaptChunk = 64;
 constexpr long long kHostChunkSweeps = 10;       // sample() to a host buffer: sweeps per launch, so copies overlap compute at this granularity
 constexpr unsigned kSmemBudget = 200u * 1024u;   // bytes of dynamic shared memory we are willing to fill with data
-constexpr unsigned kRingStageBytes = 32u * 1024u;   // TMA tile ring for columns that do not fit: 2 stages of 32 KB
+constexpr unsigned kRingStageBytes = 16u * 1024u;   // TMA tile ring for columns that do not fit: 2 stages of 16 KB (six CTAs per SM beside it)
 constexpr int kRingStages = 2;
 
 // ---- model image as the kernels see it (passed by value) ------------------------------------------------------
@@ -291,8 +291,32 @@ __device__ __forceinline__ double exp_acc(double x, unsigned tab_sa, double s) {
 
 template <int K>
 __device__ __forceinline__ void pois_rows(unsigned xsa, int rows, const double (&beta)[K], unsigned tab_sa, double& s0, double& s1) {
-  // two rows per iteration: two independent dependency chains per thread
+  // four rows per iteration: four independent dependency chains per thread (a row is K dependent FMAs, then ~10 dependent
+  // operations of the exponential; with three to six warps per scheduler that latency has to be covered inside the thread)
   int i = 0;
+  if constexpr (K <= 8) {
+    for (; i + 4 <= rows; i += 4, xsa += 32u * K) {
+      double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+      if constexpr ((K & 1) == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k += 2) {
+          const double2 a = lds_f64x2(xsa + 8u * k), b = lds_f64x2(xsa + 8u * (K + k)), c = lds_f64x2(xsa + 8u * (2 * K + k)), d = lds_f64x2(xsa + 8u * (3 * K + k));
+          e0 = fma(a.x, beta[k], e0); e1 = fma(b.x, beta[k], e1); e2 = fma(c.x, beta[k], e2); e3 = fma(d.x, beta[k], e3);
+          e0 = fma(a.y, beta[k + 1], e0); e1 = fma(b.y, beta[k + 1], e1); e2 = fma(c.y, beta[k + 1], e2); e3 = fma(d.y, beta[k + 1], e3);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          e0 = fma(lds_f64_sa(xsa + 8u * k), beta[k], e0); e1 = fma(lds_f64_sa(xsa + 8u * (K + k)), beta[k], e1);
+          e2 = fma(lds_f64_sa(xsa + 8u * (2 * K + k)), beta[k], e2); e3 = fma(lds_f64_sa(xsa + 8u * (3 * K + k)), beta[k], e3);
+        }
+      }
+      s0 = exp_acc(e0, tab_sa, s0);
+      s1 = exp_acc(e1, tab_sa, s1);
+      s0 = exp_acc(e2, tab_sa, s0);
+      s1 = exp_acc(e3, tab_sa, s1);
+    }
+  }
   for (; i + 2 <= rows; i += 2, xsa += 16u * K) {
     double e0 = 0.0, e1 = 0.0;
     if constexpr ((K & 1) == 0) {
@@ -1086,6 +1110,13 @@ __global__ void __launch_bounds__(128) amwg_ld_kernel(int word, int arity, const
 __global__ void amwg_primitive_kernel(int kind, const double* __restrict__ x, long long n, unsigned long long seed,
                                       unsigned long long chain, double* __restrict__ out) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ double tab[256];
+  if (kind == 5) {                       // the Poisson plate's table-driven exponential (exp_acc), for its accuracy test
+    for (int j = threadIdx.x; j < 256; j += blockDim.x) tab[j] = exp2((double)j * (1.0 / 256.0));
+    __syncthreads();
+    if (i < n) out[i] = exp_acc(x[i], smem_u32(tab), 0.0);
+    return;
+  }
   if (i >= n) return;
   if (kind == 0) out[i] = js_log(x[i]);
   else if (kind == 1) out[i] = js_exp(x[i]);
@@ -1455,7 +1486,7 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     // the ring is only usable by CTA-uniform models (see stage_model): do not spend shared memory (= resident CTAs) on it otherwise
     if (all > kSmemBudget && m.phase_sync && m.n_variant_comps == 0) { m.ring_smem_off = (int)smem_used; smem_used += kRingStages * kRingStageBytes; }
   }
-  const unsigned resident_budget = m.ring_smem_off >= 0 ? 96u * 1024u : kSmemBudget;    // with the ring: keep two CTAs per SM
+  const unsigned resident_budget = m.ring_smem_off >= 0 ? 36u * 1024u : kSmemBudget;    // with the ring: keep six CTAs per SM
   for (int k = 0; k < md->n_columns; ++k) {
     double* d_col = nullptr;
     if (dev_upload(s, md->columns[k].values, (size_t)md->columns[k].n, &d_col)) return bail(-1);

@@ -110,7 +110,7 @@ class Config:
             self.flop_per_draw = 131072.0 * 3
             self.hbm_bytes_per_draw = 65 * 8 + 65 * (16 + 16 + 4) / 50.0
             self.flop_note = "SURVEY 8(d): minimal 64 x 1024 + 65536 = 131072 point-terms x 3 flop (the kernel caches each group's sum of squares: 65536 point-terms per sweep)"
-            self.cpu_draws, self.probe_sweeps, self.ks_chains, self.ks_sweeps = 3, 3, 1024, 150
+            self.cpu_draws, self.probe_sweeps, self.ks_chains, self.ks_sweeps = 3, 2, 512, 10
         elif k == 5:
             K, n = 8, 1000000
             self.workload = "config 5: Poisson regression, 8 real coefs, N=1e6, 2^19 chains per GPU (2^22 on 8 GPUs)"

@@ -255,7 +255,8 @@ AMWG_API int amwg_abi_version(void);
 AMWG_API int amwg_ld_eval(int32_t op, const double* args, int32_t arity, int64_t n, double* out, int device);
 
 /* Math.log / Math.exp / the Philox uniform stream on the device, for parity tests of the primitives.
- * kind: 0 log, 1 exp, 2 stream uniform (x[i] reinterpreted: out[i] = uniform #i of chain `chain`), 3 rnorm(0,1) draw i.. */
+ * kind: 0 log, 1 exp, 2 stream uniform (x[i] reinterpreted: out[i] = uniform #i of chain `chain`), 3 rnorm(x[0], x[1]) draws of
+ * one chain, 4 Math.round, 5 the Poisson plate's table-driven exp (KS-level path; accuracy test) */
 AMWG_API int amwg_primitive_eval(int32_t kind, const double* x, int64_t n, uint64_t seed, uint64_t chain, double* out, int device);
 
 /* ---- post-path reductions on device ------------------------------------------------------------------

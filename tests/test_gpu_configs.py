@@ -35,7 +35,8 @@ def test_config2_full_size_ks_against_exact_posterior(gpu_pkg):
     (north_star's tolerance) against the exact posterior; the reference's own tests compare against JAGS at p > 0.01."""
     x = config2_data()
     s = gpu_pkg.mcmc.AmwgSampler(models.PARAMS_NORM, models.norm_post_readme(gpu_pkg.ld), x.tolist(), {"chains": 1 << 20, "seed": 0})
-    assert s.program_summary()[-1] == "plate NORM_IID n=1024"
+    assert "plate NORM_IID n=1024" in s.program_summary()
+    assert s.jit_status()[0], s.jit_status()[1]            # 2^20 chains: the run-time specialised sweep (the production path)
     s.burn(3000)
     d = s.sample(1)
     (gm, cm), (gs, cs) = _grid_posterior_cdfs(x)
@@ -145,7 +146,7 @@ def test_statistics_sweep_on_the_headline_shape_with_int_bounds_thin_and_derived
     from conftest import config2_data
     mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
     data = config2_data().tolist()
-    two = (("stat", {"AMWG_STAT_LOWERING": "2"}), ("full", {"AMWG_STAT_LOWERING": "2", "AMWG_STAT_SWEEP": "0"}), ("plain", {}))
+    two = (("stat", {}), ("full", {"AMWG_STAT_SWEEP": "0"}), ("plain", {"AMWG_STAT_LOWERING": "0"}))
     pars = {"mu": {"type": "real"}, "sigma": {"type": "real", "lower": 0}}
     out = _run_modes(gpu_pkg, two, lambda: mcmc.AmwgSampler(pars, models.norm_post_test(ld), data, {"chains": 1000, "seed": 3, "thin": 3}), 230, 100)
     assert out["stat"]["mu"].shape == (34, 1000) and set(out["stat"]) == {"mu", "sigma", "var"}
@@ -229,3 +230,21 @@ def test_data_larger_than_shared_memory_is_served_from_l2(gpu_pkg):
     d = s.sample(1)
     assert abs(d["mu"].mean() - x.mean()) < 0.005 and abs(d["sigma"].mean() - x.std(ddof=1)) < 0.01
     assert abs(d["mu"].std() - x.std() / np.sqrt(x.size)) < 0.004
+
+
+def test_poisson_plate_exponential_is_accurate(gpu_pkg):
+    """The POIS_LOGLIN plate sums exp(eta_i) with a table-driven exponential (2^(j/256) x degree-4 polynomial, csrc exp_acc): within
+    2 ulp of the correctly rounded value over the whole range a linear predictor can take, exact at 0, library exp() beyond +-690."""
+    import ctypes as C
+    L = gpu_pkg._ffi.lib()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-30, 30, 200000), rng.uniform(-689, 689, 50000), rng.normal(0, 1e-6, 1000),
+                        [0.0, -0.0, 1.0, -1.0, 689.9, -689.9, 700.0, -745.0, 710.0, np.inf, -np.inf, np.nan]])
+    out = np.empty_like(x)
+    assert L.amwg_primitive_eval(5, x.ctypes.data, x.size, 0, 0, out.ctypes.data, 0) == 0
+    want = np.exp(x)
+    fin = np.isfinite(want) & (want > 0)
+    ulp = np.abs(out[fin] - want[fin]) / np.spacing(want[fin])
+    assert ulp.max() <= 2.0, ulp.max()
+    assert out[x == 0.0].tolist() == [1.0, 1.0]
+    assert np.isnan(out[-1]) and out[-2] == 0.0 and out[-3] == np.inf
