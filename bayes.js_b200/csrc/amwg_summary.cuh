@@ -153,17 +153,31 @@ extern "C" int amwg_summary_moments(int device, const double* dev_samples, int64
   if (!dev_samples || !host_stats) return fail("amwg_summary_moments: null pointer");
   CUDA_TRY(cudaSetDevice(device));
   const unsigned bx = (unsigned)std::min<int64_t>((chains + 255) / 256, 148 * 8);     // depends on `chains` only: a fixed merge order
+  // scratch that lives as long as the process (per device, grown on demand): no cudaMalloc / cudaFree on the path of a call
+  struct Scratch { void* p = nullptr; size_t bytes = 0; };
+  static Scratch scratch[64];
+  static std::mutex scratch_mu;
+  const size_t need_partial = (size_t)entries * bx * sizeof(summary::Moments), need_out = (size_t)entries * 4 * sizeof(double);
+  const size_t need = ((need_partial + 255) / 256) * 256 + need_out;
   summary::Moments* partial = nullptr;
   double* d_out = nullptr;
-  cudaError_t e = cudaMalloc(&partial, (size_t)entries * bx * sizeof(summary::Moments));
-  if (e == cudaSuccess) e = cudaMalloc(&d_out, (size_t)entries * 4 * sizeof(double));
-  if (e == cudaSuccess) {
-    summary::amwg_chain_moments_kernel<<<dim3(bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, partial);
-    summary::amwg_merge_moments_kernel<<<(unsigned)entries, 1024>>>(partial, (int)bx, d_out);
-    e = cudaGetLastError();
+  {
+    std::lock_guard<std::mutex> lock(scratch_mu);
+    if (device < 0 || device >= 64) return fail("amwg_summary_moments: device index out of range");
+    Scratch& sc = scratch[device];
+    if (sc.bytes < need) {
+      if (sc.p) cudaFree(sc.p);
+      sc.p = nullptr; sc.bytes = 0;
+      CUDA_TRY(cudaMalloc(&sc.p, need));
+      sc.bytes = need;
+    }
+    partial = reinterpret_cast<summary::Moments*>(sc.p);
+    d_out = reinterpret_cast<double*>(reinterpret_cast<char*>(sc.p) + ((need_partial + 255) / 256) * 256);
   }
-  if (e == cudaSuccess) e = cudaMemcpy(host_stats, d_out, (size_t)entries * 4 * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(partial); cudaFree(d_out);
+  summary::amwg_chain_moments_kernel<<<dim3(bx, (unsigned)entries), 256>>>(dev_samples, rows, entries, chains, partial);
+  summary::amwg_merge_moments_kernel<<<(unsigned)entries, 1024>>>(partial, (int)bx, d_out);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpy(host_stats, d_out, need_out, cudaMemcpyDeviceToHost);
   if (e != cudaSuccess) return fail(std::string("amwg_summary_moments: ") + cudaGetErrorString(e));
   return 0;
 }

@@ -5,7 +5,7 @@
  *     new mcmc.AmwgSampler(params, log_post, data, options)   mcmc.js:1090-1092, 940-966
  *     .burn(n) .sample(n) .step() .thin(k) .monitor(names)     mcmc.js:985-1055
  *     .start_adaptation() .stop_adaptation() .info()           mcmc.js:1060-1073, 977-980
- * This header is what a Node N-API addon (js/amwg_napi.cc) or any other host
+ * This header is what the Node N-API addon (js/amwg_napi.cc), the Python host (bayes.js_b200/_ffi.py) or any other host
  * binds instead.  Plain pointers and sizes only; every call returns 0 or a negative status and
  * amwg_last_error() gives the message the JS shim re-throws as a bare string (the reference
  * throws strings, mcmc.js:165,299,315,340,445,490,495,636,746,790,867,972).

@@ -248,3 +248,21 @@ def test_poisson_plate_exponential_is_accurate(gpu_pkg):
     assert ulp.max() <= 2.0, ulp.max()
     assert out[x == 0.0].tolist() == [1.0, 1.0]
     assert np.isnan(out[-1]) and out[-2] == 0.0 and out[-3] == np.inf
+
+
+def test_pooled_oracle_ks_on_the_production_path(gpu_pkg, orc):
+    """KS of pooled GPU draws against >= 1e5 (nearly independent) pooled draws of the CPU restatement of mcmc.js on the
+    same model and data -- the reference sampler itself as the yardstick, beside the exact-posterior KS above. The GPU side is the
+    production lowering (statistics sweep, run-time specialised kernel); the oracle evaluates log_post twice per step, term by term."""
+    x = np.random.default_rng(64).normal(184.5, 4.5, 64)
+    P = models.PARAMS_NORM
+    s = gpu_pkg.mcmc.AmwgSampler(P, models.norm_post_readme(gpu_pkg.ld), x.tolist(), {"chains": 1 << 17, "seed": 5})
+    assert s.jit_status()[0], s.jit_status()[1]
+    s.burn(2000)
+    g = s.sample(1)
+    ref = orc.run_model("norm_readme", x, P, chains=512, seed=99, burn=2000, sample=4000, thin=20, threads=8)      # 512 x 200 kept draws
+    for name in ("mu", "sigma"):
+        a, b = np.sort(g[name].reshape(-1)), np.sort(ref[name].reshape(-1))
+        allv = np.concatenate([a, b])
+        d = np.max(np.abs(np.searchsorted(a, allv, side="right") / a.size - np.searchsorted(b, allv, side="right") / b.size))
+        assert b.size >= 100000 and d < 0.01, (name, d)
