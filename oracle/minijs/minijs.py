@@ -846,11 +846,15 @@ class Interpreter:
     def run(self, src: str, this=None):
         ast = Parser(tokenize(src)).program()
         self._hoist(ast[1], self.global_env)
-        self._this_stack = [this if this is not None else self.global_obj]
+        if not hasattr(self, "_this_stack"):
+            self._this_stack = []
+        self._this_stack.append(this if this is not None else self.global_obj)      # run() may nest (a native `require` loads a module)
         try:
             self.exec_block(ast[1], self.global_env)
         except _Return:
             pass
+        finally:
+            self._this_stack.pop()
 
     def get_global(self, name):
         return self.global_env.vars.get(name, undefined)

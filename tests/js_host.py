@@ -33,6 +33,19 @@ class JsHost:
             return self.modules[key]
         it.set_global("require", it.make_native("require", require))
 
+        def clone(this, a):                                         # snapshot of a live value (step() returns the caller's own state object)
+            def cp(v):
+                if isinstance(v, JSArray):
+                    return it.new_array([cp(x) for x in v.items])
+                if isinstance(v, JSObject) and not isinstance(v, JSFunction):
+                    o = it.new_object()
+                    for k2, x in v.props.items():
+                        o.put(k2, cp(x))
+                    return o
+                return v
+            return cp(a[0])
+        it.set_global("JSON_clone", it.make_native("JSON_clone", clone))
+
     def load(self, key):
         it = self.it
         mod = it.new_object()

@@ -212,3 +212,35 @@ def test_js_many_chains_and_specialised_kernel(host, monkeypatch):
     mu = np.asarray(d["mu"])
     assert mu.shape == (20, 512)
     assert abs(mu.mean() - x.mean()) < 0.05 and abs(np.asarray(d["sigma"]).mean() - x.std(ddof=1)) < 0.08
+
+
+@pytest.mark.parametrize("case", G["steppers"], ids=lambda c: f"{c['class']}-chain{c['chain']}")
+def test_js_standalone_steppers_match_the_reference(case, host):
+    """mcmc.RealMetropolisStepper & co from JavaScript, constructed and stepped with the very JS text the golden generator ran
+    against the unmodified reference (tests/test_mcmc_js.R:55-142 use the steppers this way)."""
+    it = host.it
+    it.set_global("X", to_js(it, [float(v) for v in gu.NB12]))
+    host.run("""
+      var params_complex_model = {p1: {type: "real", lower: 0, upper: 1}, n1: {type: "int", lower: 1, init: 1}, m: {type: "binary"}};
+      var state = %s;
+      var stepper_options = %s || {};
+      stepper_options.seed = %d; stepper_options.first_chain = %d; stepper_options.faithful = true;
+      var stepper = new mcmc.%s(%s, state, function () { return %s; }, stepper_options);
+    """ % (case["state_js"], case["options_js"] or "null", case["seed"], case["chain"], case["class"], case["params_js"], case["posterior_js"]))
+    results = iter(case["results"])
+    for step in case["script"]:
+        if step[0] == "step":
+            host.run("var outs = []; for (var i = 0; i < %d; i++) { outs.push(JSON_clone(stepper.step())); }" % step[1])
+            got, want = to_py(host.get("outs")), gu.unhex(next(results))
+            if case["class"] == "AmwgStepper":
+                for k in want[0]:
+                    assert gu.same([g[k] for g in got], [w[k] for w in want]), k
+            else:
+                assert gu.same(_nested(got), _nested(want))
+        elif step[0] == "stop_adaptation":
+            host.run("stepper.stop_adaptation();")
+        elif step[0] == "start_adaptation":
+            host.run("stepper.start_adaptation();")
+    st = to_py(host.get("state"))
+    for name, want in gu.unhex(case["final_state"]).items():
+        assert gu.same(_nested(st[name]).reshape(-1), _nested(want).reshape(-1)), name
