@@ -455,13 +455,12 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
   if (!md->comp_prog || md->n_terms <= 0 || md->stat_prog < 0) return "the model has no pre-evaluated statistics";
   if (md->n_variant_comps > 0) return "variant programs";
   const int D = md->n_comp, P = md->n_params, NT = md->n_terms;
-  if (D > 65535 || P > 16) return "too many components / parameters";
+  if (D > 65535 || P > 255) return "too many components / parameters";
   int max_dim0 = 1;
   for (int p = 0; p < P; ++p) {
     if (md->params[p].type == AMWG_BINARY) return "binary parameter";
     if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, md->params[p].dim0);
   }
-  if (max_dim0 > 256) return "dim[0] > 256";
   std::string err;
 
   // ---- the statistics pass: PLATE_SS entries of stat_prog

@@ -95,7 +95,7 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
   g.init(a.rng_n[chain]);
   unsigned long long perm = a.perm[chain];
 #if JMAX_DIM0 > 1
-  unsigned char order[JMAX_DIM0];
+  unsigned char order[JMAX_DIM0 < kLocalOrder ? JMAX_DIM0 : kLocalOrder];
 #endif
 #if JSTREAM
   unsigned ring_fills = 0;                                      // tiles streamed so far by this CTA (stage = fills % stages)
@@ -134,25 +134,25 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
 #if JP > 1
     for (int i = JP - 1; i > 0; --i) {                          // shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
       const int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-      const unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
-      perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
-      perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+      perm_swap(a, perm, chain, i, j, valid);
     }
 #endif
     int pos = 0;
 #pragma unroll 1
     for (int slot = 0; slot < JP; ++slot) {
-      const int p = (JP > 1) ? (int)((perm >> (4 * slot)) & 15ull) : 0;
+      const int p = (JP > 1) ? perm_get(a, perm, chain, slot) : 0;
       const int n_comp = jp_ncomp(p), off = jp_off(p), ptype = jp_type(p);
       const double lower = jp_lower(p), upper = jp_upper(p);
 #if JMAX_DIM0 > 1
       const int dim0 = jp_dim0(p);
       const int inner = n_comp / dim0;
       if (n_comp > 1) {                                         // nested_array_random_apply: top level only (mcmc.js:246-252)
-        for (int i = 0; i < dim0; ++i) order[i] = (unsigned char)i;
+        for (int i = 0; i < dim0; ++i) ord_set(a, order, chain, dim0, i, i, valid);
         for (int i = dim0 - 1; i > 0; --i) {
           const int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-          const unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
+          const int t = ord_get(a, order, chain, dim0, i);
+          ord_set(a, order, chain, dim0, i, ord_get(a, order, chain, dim0, j), valid);
+          ord_set(a, order, chain, dim0, j, t, valid);
         }
       }
 #endif
@@ -160,7 +160,7 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
       for (int r = 0; r < n_comp; ++r, ++pos) {
         int c = off;
 #if JMAX_DIM0 > 1
-        if (n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        if (n_comp > 1) c += ord_get(a, order, chain, dim0, r / inner) * inner + (r % inner);
 #endif
         const double cur = ST(c);
         double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[(unsigned long long)c * C + chain]);   // generate_proposal (mcmc.js:519, 577-579 / 596-598)

@@ -35,8 +35,8 @@
 namespace amwg {
 
 constexpr int kMaxColumns = 32;
-constexpr int kMaxParams = 16;       // substepper order is packed 4 bits per named parameter
-constexpr int kMaxDim0 = 256;        // top-level visit order of a multi-dim parameter (uint8 per entry)
+constexpr int kMaxParams = 255;      // substepper order: packed 4 bits per named parameter up to 16, a byte per entry in global memory beyond
+constexpr int kMaxDim0 = 65535;      // top-level visit order of a multi-dim parameter: local bytes up to 256, 16-bit rows in global memory beyond
 constexpr int kMaxDerived = 32;
 constexpr int kStack = 32;          // operand stack of the interpreter; validate_model rejects programs that need more
 #ifndef AMWG_THREADS
@@ -649,7 +649,8 @@ __global__ void __launch_bounds__(kThreads) amwg_init_kernel(ModelDev m, ChainAr
       a.acc[(unsigned long long)c * a.C + chain] = 0;
     }
     unsigned long long perm = 0;
-    for (int p = 0; p < m.n_params; ++p) perm |= (unsigned long long)p << (4 * p);
+    if (a.perm_ext) for (int p = 0; p < m.n_params; ++p) a.perm_ext[(unsigned long long)p * a.C + chain] = (unsigned char)p;
+    else for (int p = 0; p < m.n_params; ++p) perm |= (unsigned long long)p << (4 * p);
     a.perm[chain] = perm;
     a.rng_n[chain] = 0;
   }
@@ -706,7 +707,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
   unsigned long long perm = a.perm[chain];
   double curr = a.curr_lp[chain];
   const int P = m.n_params;
-  unsigned char order[kMaxDim0];
+  unsigned char order[kLocalOrder];
 
   // `i % thin === 0` (mcmc.js:1021) without a 64-bit division per sweep: position inside the thinning interval and next row
   long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
@@ -736,25 +737,25 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
     // -- AmwgStepper.step: shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
     for (int i = P - 1; i > 0; --i) {
       int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-      unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
-      perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
-      perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+      perm_swap(a, perm, chain, i, j, valid);
     }
     for (int slot = 0; slot < P; ++slot) {
-      const amwg_param& pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];   // read from shared memory where needed: not kept in registers
+      const amwg_param& pa = ctx.params[perm_get(a, perm, chain, slot)];   // read from shared memory where needed: not kept in registers
       const int n_rounds = pa.n_comp;
       const int inner = pa.n_comp / pa.dim0;
       if (pa.n_comp > 1) {
         // nested_array_random_apply: fresh identity, shuffled, top level only (mcmc.js:246-252)
-        for (int i = 0; i < pa.dim0; ++i) order[i] = (unsigned char)i;
+        for (int i = 0; i < pa.dim0; ++i) ord_set(a, order, chain, pa.dim0, i, i, valid);
         for (int i = pa.dim0 - 1; i > 0; --i) {
           int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-          unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
+          const int t = ord_get(a, order, chain, pa.dim0, i);
+          ord_set(a, order, chain, pa.dim0, i, ord_get(a, order, chain, pa.dim0, j), valid);
+          ord_set(a, order, chain, pa.dim0, j, t, valid);
         }
       }
       int block_slot = -1;
       if constexpr (CACHE) {
-        const int pidx = (int)((perm >> (4 * slot)) & 15ull);
+        const int pidx = perm_get(a, perm, chain, slot);
         for (int k = 0; k < m.n_block_params; ++k) if (m.block_params[k] == pidx) block_slot = k;
       }
       // A block-stepped parameter (amwg.h block_params) takes ONE round for all its components; otherwise one round per component.
@@ -767,7 +768,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
         // ---- phase 1: propose
         if (sync) __syncthreads();
         int c = pa.comp_offset;
-        if (!is_block && pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        if (!is_block && pa.n_comp > 1) c += ord_get(a, order, chain, pa.dim0, r / inner) * inner + (r % inner);
         const unsigned long long ci = (unsigned long long)c * C;
         double cur = 0.0, prop = 0.0;
         bool need;
@@ -775,7 +776,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           // proposals and accept uniforms of every component, in the chain's visiting order: the Math.random() calls of
           // mcmc.js:519-528 in their original order (a uniform is only drawn for an in-bounds proposal)
           for (int q = 0; q < n_rounds; ++q) {
-            const int cq = pa.comp_offset + (int)order[q / inner] * inner + (q % inner);
+            const int cq = pa.comp_offset + ord_get(a, order, chain, pa.dim0, q / inner) * inner + (q % inner);
             const unsigned long long cqi = (unsigned long long)cq * C + chain;
             const double curq = a.state[cqi];
             double pq = js_rnorm(g, a.seed, gchain, curq, a.psd[cqi]);
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_sweep_kerne
           // terms with c's terms taken from the candidates -- exactly what the per-component program adds
           const int* tbc = ctx.tbc + block_slot * m.n_terms;
           for (int q = 0; q < n_rounds; ++q) {
-            const int cq = pa.comp_offset + (int)order[q / inner] * inner + (q % inner);
+            const int cq = pa.comp_offset + ord_get(a, order, chain, pa.dim0, q / inner) * inner + (q % inner);
             const unsigned long long cqi = (unsigned long long)cq * C + chain;
             const double coin = a.bcoin[cqi];
             if (coin < 0.0) continue;                        // out of bounds: rejected without evaluation (mcmc.js:520-522)
@@ -941,7 +942,7 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
   g.init(a.rng_n[chain]);
   unsigned long long perm = a.perm[chain];
   double curr = a.curr_lp[chain];
-  unsigned char order[kMaxDim0];
+  unsigned char order[kLocalOrder];
 
   long long rec_phase = sa.record ? sa.sample_i0 % sa.thin : 0;
   long long row = sa.record ? (sa.sample_i0 + sa.thin - 1) / sa.thin : 0;
@@ -970,24 +971,24 @@ __global__ void __launch_bounds__(kSyncThreads, AMWG_MINBLOCKS) amwg_stat_sweep_
     if (m.stat_barriers) __syncthreads();
     for (int i = P - 1; i > 0; --i) {                           // shuffle_array(this.substeppers), in place (mcmc.js:887, 228-236)
       int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-      unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
-      perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
-      perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+      perm_swap(a, perm, chain, i, j, valid);
     }
     int pos = 0;
     for (int slot = 0; slot < P; ++slot) {
-      const amwg_param& pa = ctx.params[(int)((perm >> (4 * slot)) & 15ull)];
+      const amwg_param& pa = ctx.params[perm_get(a, perm, chain, slot)];
       const int inner = pa.n_comp / pa.dim0;
       if (pa.n_comp > 1) {                                      // nested_array_random_apply: top level only (mcmc.js:246-252)
-        for (int i = 0; i < pa.dim0; ++i) order[i] = (unsigned char)i;
+        for (int i = 0; i < pa.dim0; ++i) ord_set(a, order, chain, pa.dim0, i, i, valid);
         for (int i = pa.dim0 - 1; i > 0; --i) {
           int j = (int)floor(g.next(a.seed, gchain) * (i + 1));
-          unsigned char t = order[i]; order[i] = order[j]; order[j] = t;
+          const int t = ord_get(a, order, chain, pa.dim0, i);
+          ord_set(a, order, chain, pa.dim0, i, ord_get(a, order, chain, pa.dim0, j), valid);
+          ord_set(a, order, chain, pa.dim0, j, t, valid);
         }
       }
       for (int r = 0; r < pa.n_comp; ++r, ++pos) {
         int c = pa.comp_offset;
-        if (pa.n_comp > 1) c += (int)order[r / inner] * inner + (r % inner);
+        if (pa.n_comp > 1) c += ord_get(a, order, chain, pa.dim0, r / inner) * inner + (r % inner);
         const double cur = sp[(unsigned long long)c * ws];
         double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[(unsigned long long)c * C + chain]);   // generate_proposal (mcmc.js:519, 577-579 / 596-598)
         if (pa.type == AMWG_INT) prop = js_round(prop);
@@ -1202,7 +1203,7 @@ struct JitArgsHost {
 static int validate_model(const amwg_model* md) {
   if (!md) return fail("amwg_create: model is NULL");
   if (md->abi_version != AMWG_ABI_VERSION) return fail("amwg_create: ABI version mismatch");
-  if (md->n_params < 1 || md->n_params > kMaxParams) return fail("amwg_create: between 1 and 16 named parameters are supported");
+  if (md->n_params < 1 || md->n_params > kMaxParams) return fail("amwg_create: between 1 and 255 named parameters are supported");
   if (md->n_columns > kMaxColumns) return fail("amwg_create: at most 32 data columns are supported");
   if (md->n_derived > kMaxDerived) return fail("amwg_create: at most 32 derived quantities are supported");
   int D = 0;
@@ -1211,7 +1212,7 @@ static int validate_model(const amwg_model* md) {
     if (pa.lower > pa.upper) return fail("Can not initialize parameter where lower bound > upper bound");   // mcmc.js:314-316
     if (pa.type < 0 || pa.type > 2) return fail("AmwgStepper can't handle parameter with this type");        // mcmc.js:867
     if (pa.n_comp < 1 || pa.dim0 < 1 || pa.n_comp % pa.dim0) return fail("amwg_create: bad parameter dimensions");
-    if (pa.dim0 > kMaxDim0) return fail("amwg_create: dim[0] > 256 is not supported");
+    if (pa.dim0 > kMaxDim0) return fail("amwg_create: dim[0] > 65535 is not supported");
     if (pa.comp_offset != D) return fail("amwg_create: comp_offset must be the running component count");
     if (pa.type == AMWG_BINARY)
       for (int c = 0; c < pa.n_comp; ++c)
@@ -1525,6 +1526,14 @@ extern "C" int amwg_create(const amwg_model* md, uint64_t n_chains, uint64_t fir
     return bail(-1);
   a.tval = a.tcand = a.bprop = a.bcoin = nullptr;
   a.vseq = nullptr;
+  a.perm_ext = nullptr;
+  a.order_ext = nullptr;
+  {
+    int max_dim0 = 1;
+    for (const auto& pa : s->params) if (pa.n_comp > 1) max_dim0 = std::max(max_dim0, pa.dim0);
+    if (s->P > 16 && dev_alloc(s, (size_t)s->P * (size_t)n_chains, &a.perm_ext)) return bail(-1);
+    if (max_dim0 > kLocalOrder && dev_alloc(s, (size_t)max_dim0 * (size_t)n_chains, &a.order_ext)) return bail(-1);
+  }
   if (m.n_terms > 0) {
     // one allocation, rows [tval n_terms | tcand n_terms | bprop D | bcoin D] x C: amwg_stat_sweep_kernel addresses them as one block
     const size_t TC = (size_t)m.n_terms * (size_t)n_chains;

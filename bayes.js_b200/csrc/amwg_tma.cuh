@@ -18,6 +18,8 @@ struct ChainArrays {
   double* bcoin;          // [D][C] block steps: the accept uniform drawn for it (-1: proposal out of bounds, no uniform drawn)
   unsigned short* vseq;   // [D][C] pre-evaluated statistics: the components in this sweep's visiting order
   unsigned long long* perm;   // [C] substepper order, 4 bits per named parameter (persists: mcmc.js:887 shuffles in place)
+  unsigned char* perm_ext;    // [P][C] the same order, one byte per entry, for models with more than 16 named parameters (else nullptr)
+  unsigned short* order_ext;  // [max dim0][C] visiting order of a multi-dim parameter whose dim[0] exceeds 256 (else nullptr)
   unsigned long long* rng_n;  // [C] Math.random() calls consumed so far
   unsigned long long C;
   unsigned long long first_chain;
@@ -33,6 +35,36 @@ struct SweepArgs {
   const int* monitor;      // global [n_monitor]
   double* out;             // [row][monitor][chain]
 };
+
+// ---- the two permutations of a sweep ------------------------------------------------------------------------------------------
+// AmwgStepper shuffles its substeppers IN PLACE every sweep (mcmc.js:887): the order persists. Up to 16 named parameters it is one
+// 64-bit word per chain, kept in a register; beyond that a byte per entry in global memory. A multi-dim parameter's visiting order
+// (mcmc.js:246-252, a fresh shuffle every sweep) is a 256-byte local array, or 16-bit rows in global memory for dim[0] > 256.
+// Threads that shadow the last chain (CTA-uniform data passes) never write the global forms; what they read is the owner's array
+// at some moment -- always valid indices, and a shadow's results are discarded.
+constexpr int kLocalOrder = 256;
+__device__ __forceinline__ int perm_get(const ChainArrays& a, unsigned long long perm, unsigned long long chain, int i) {
+  return a.perm_ext ? (int)a.perm_ext[(unsigned long long)i * a.C + chain] : (int)((perm >> (4 * i)) & 15ull);
+}
+__device__ __forceinline__ void perm_swap(const ChainArrays& a, unsigned long long& perm, unsigned long long chain, int i, int j, bool wr) {
+  if (a.perm_ext) {
+    if (!wr) return;
+    unsigned char* pi = a.perm_ext + (unsigned long long)i * a.C + chain;
+    unsigned char* pj = a.perm_ext + (unsigned long long)j * a.C + chain;
+    const unsigned char t = *pi; *pi = *pj; *pj = t;
+    return;
+  }
+  const unsigned long long vi = (perm >> (4 * i)) & 15ull, vj = (perm >> (4 * j)) & 15ull;
+  perm = (perm & ~(15ull << (4 * i))) | (vj << (4 * i));
+  perm = (perm & ~(15ull << (4 * j))) | (vi << (4 * j));
+}
+__device__ __forceinline__ int ord_get(const ChainArrays& a, const unsigned char* loc, unsigned long long chain, int dim0, int i) {
+  return dim0 <= kLocalOrder ? (int)loc[i] : (int)a.order_ext[(unsigned long long)i * a.C + chain];
+}
+__device__ __forceinline__ void ord_set(const ChainArrays& a, unsigned char* loc, unsigned long long chain, int dim0, int i, int v, bool wr) {
+  if (dim0 <= kLocalOrder) loc[i] = (unsigned char)v;
+  else if (wr) a.order_ext[(unsigned long long)i * a.C + chain] = (unsigned short)v;
+}
 
 // ---- TMA 1-D bulk copy + mbarrier (sm_90+; SASS: UBLKCP / SYNCS) -------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }

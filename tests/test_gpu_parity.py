@@ -245,3 +245,46 @@ def test_log_post_method_and_the_rest_of_the_ld_surface(gpu_pkg, orc):
     assert abs(got - want) <= 1e-13 * abs(want), (got, want)
     s.burn(50)
     assert np.isfinite(s.log_post()) and 0 <= s.state["x"] <= 1
+
+
+def test_more_than_16_named_parameters_and_dim0_beyond_256(gpu_pkg, orc):
+    """The reference has no limit on the number of named parameters or on dim[0] (mcmc.js:844-881). Up to 16 / 256 the two
+    permutations of a sweep live in a register / a local array; beyond, in per-chain global arrays (amwg_tma.cuh perm_get / ord_get).
+    Same draws as the oracle, bit for bit, including the in-place substepper shuffle that persists across sweeps."""
+    ld, mcmc = gpu_pkg.ld, gpu_pkg.mcmc
+    O = orc.lib()
+    P = 23
+    params = {"t%d" % k: ({"type": "real"} if k % 3 else {"type": "int", "lower": -50, "upper": 50}) for k in range(P)}
+
+    def lp_many(state, d=None):
+        lp = 0
+        for k in range(P):
+            lp += ld.norm(state["t%d" % k], 0.5 * k, 1 + 0.1 * k)
+        return lp
+    s = mcmc.AmwgSampler(params, lp_many, None, {"chains": 3, "seed": 41, "first_chain": 7})
+    got = s.sample(60)
+    for c in range(3):
+        o = orc.OracleSampler(lambda st: sum(O.orc_ld_norm(st[k], 0.5 * k, 1 + 0.1 * k) for k in range(P)), None, params, seed=41, chain=7 + c)
+        ref = o.sample(60)
+        for k in range(P):
+            assert np.array_equal(got["t%d" % k][:, c], ref["t%d" % k]), (c, k)
+    J = 300
+    params = {"x": {"type": "real", "dim": [J]}, "s": {"type": "real", "lower": 0}}
+
+    def lp_wide(state, d=None):
+        lp = ld.gamma(state.s, 2, 1)
+        for j in range(J):
+            lp += ld.norm(state.x[j], 0.01 * j, state.s)
+        return lp
+    s = mcmc.AmwgSampler(params, lp_wide, None, {"chains": 2, "seed": 43})
+    got = s.sample(25)
+
+    def f(st):
+        v = O.orc_ld_gamma(st[J], 2, 1)
+        for j in range(J):
+            v += O.orc_ld_norm(st[j], 0.01 * j, st[J])
+        return v
+    for c in range(2):
+        o = orc.OracleSampler(f, None, params, seed=43, chain=c)
+        ref = o.sample(25)
+        assert np.array_equal(got["x"][:, c], ref["x"]) and np.array_equal(got["s"][:, c], ref["s"]), c
