@@ -553,7 +553,9 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
       double eff; int r_need;
       if (ctas <= cap) { const double per_sm = std::ceil(ctas / sm_count); eff = ((double)n_chains / sm_count) / (per_sm * t); r_need = (int)per_sm; }
       else { eff = ctas / (std::ceil(ctas / cap) * cap) * ((double)n_chains / (ctas * t)); r_need = r_max; }
-      if (eff > best_eff + 0.01) { best_eff = eff; best_t = t; best_r = r_need; best_ws = ws_smem; }
+      // 128-thread CTAs are the default; another size has to fill the SMs a good deal more evenly to win (config 4 at 2^16 chains:
+      // 224 x 2 CTAs/SM is 14 % better balanced than 128 x 4 and measured 6 % SLOWER -- more, smaller CTAs overlap their phases)
+      if (eff > best_eff + (best_t == 0 ? 0.0 : 0.15)) { best_eff = eff; best_t = t; best_r = r_need; best_ws = ws_smem; }
       if (forced_t) break;
     }
     if (!best_t) return "no launch shape fits";
@@ -703,7 +705,25 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
 
   unsigned long long res_total = 0;
   for (int k = 0; k < pl.n_res; ++k) res_total += (unsigned)pl.res_bytes[k];
+  // JBLOCK: the largest multi-dim parameter whose components never share a term or a statistic (pairwise disjoint touch lists)
+  int jblock = -1;
+  for (int p = 0, best = 7; p < P; ++p) {
+    const amwg_param& pa = md->params[p];
+    if (pa.n_comp <= best) continue;
+    bool indep = true;
+    std::vector<int> owner((size_t)NT, -1);
+    for (int c = pa.comp_offset; c < pa.comp_offset + pa.n_comp && indep; ++c)
+      for (int k = md->touch_off[c]; k < md->touch_off[c + 1]; ++k) {
+        int& o = owner[(size_t)md->touch_terms[k]];
+        if (o >= 0 && o != c) { indep = false; break; }
+        o = c;
+      }
+    if (indep) { jblock = p; best = pa.n_comp; }
+  }
+  if (const char* e = getenv("AMWG_JIT_BLOCK")) { if (atoi(e) == 0) jblock = -1; }
+  const bool jblock_free = jblock >= 0 && md->params[jblock].lower == -INFINITY && md->params[jblock].upper == INFINITY;
   std::ostringstream pre;
+  pre << "#define JBLOCK " << jblock << "\n#define JBLOCK_FREE " << (jblock_free ? 1 : 0) << "\n";
   pre << "#define JD " << D << "\n#define JP " << P << "\n#define JNT " << NT << "\n#define JNSUM " << md->n_sum_terms << "\n"
       << "#define JTHREADS " << pl.threads << "\n#define JMINB " << pl.minblocks << "\n#define JWS_SMEM " << pl.ws_smem << "\n#define JWS_OFF " << pl.ws_off << "\n"
       << "#define JN_DERIVED " << md->n_derived << "\n#define JMAX_DIM0 " << max_dim0 << "\n#define JMAXCOL " << kMaxColumns << "\n"
@@ -711,6 +731,10 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
       << "#define JSTREAM " << (pl.stream_col >= 0 ? 1 : 0) << "\n#define JS_COL " << std::max(pl.stream_col, 0) << "\n#define JS_BEGIN " << s_begin << "\n#define JS_TOTAL " << s_total << "\n"
       << "#define JN_SSTAT " << s_entries.size() << "\n#define JRING_OFF " << pl.ring_off << "u\n#define JRING_STAGES " << pl.ring_stages << "\n#define JRING_TILE " << pl.ring_tile << "\n"
       << "#define JNORM_C0 " << lit(norm_c0) << "\n#define AMWG_REAL 0\n#define AMWG_INT 1\n#define AMWG_BINARY 2\n";
+  // accumulators of the plate loop: four (eight measured 5 % slower on config 4 at 3.5 warps per scheduler, profiles/r02_config4_tuning.txt)
+  int nacc = 4;
+  if (const char* e = getenv("AMWG_JIT_NACC")) { int v = atoi(e); if (v == 4 || v == 8) nacc = v; }
+  pre << "#define AMWG_NACC " << nacc << "\n";
   src.prelude = pre.str();
   funcs << tables.str() << step.str() << extra.str() << dfun.str() << "}  // namespace amwg\n";
   src.generated = funcs.str();

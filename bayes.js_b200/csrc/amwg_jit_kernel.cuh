@@ -162,6 +162,17 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
 #if JMAX_DIM0 > 1
         if (n_comp > 1) c += ord_get(a, order, chain, dim0, r / inner) * inner + (r % inner);
 #endif
+#if JBLOCK >= 0 && JBLOCK_FREE
+        if (p == JBLOCK) {
+          // an unbounded parameter always draws its accept uniform: the sweep's random numbers do not depend on its value or its
+          // proposal scale. Only the ratio v / u of the accepted Leva trial is kept here; the proposal is finished below in index
+          // order, where the rows of state and scale are read contiguously instead of one scattered row per lane.
+          const double z = js_rnorm_ratio(g, a.seed, gchain);
+          const double coin = g.next(a.seed, gchain);
+          if (wr) { BP(c) = z; BC(c) = coin; }
+          continue;
+        }
+#endif
         const double cur = ST(c);
         double prop = js_rnorm(g, a.seed, gchain, cur, a.psd[(unsigned long long)c * C + chain]);   // generate_proposal (mcmc.js:519, 577-579 / 596-598)
         if (ptype == AMWG_INT) prop = js_round(prop);
@@ -174,6 +185,19 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
         }
       }
     }
+#if JBLOCK >= 0 && JBLOCK_FREE
+    {
+      const int n_b = jp_ncomp(JBLOCK), off_b = jp_off(JBLOCK);
+      const bool is_int = jp_type(JBLOCK) == AMWG_INT;
+#pragma unroll 4
+      for (int r = 0; r < n_b; ++r) {                           // (v / u) * sd + mean, the last two operations of rnorm (mcmc.js:53)
+        const int c = off_b + r;
+        double prop = BP(c) * a.psd[(unsigned long long)c * C + chain] + ST(c);
+        if (is_int) prop = js_round(prop);
+        if (wr) BP(c) = prop;
+      }
+    }
+#endif
     // ---- (b) one pass over the data: every plate statistic at the proposals -> candidate slots
 #if JN_RSTAT > 0
 #pragma unroll 1
@@ -236,20 +260,60 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
       ring_fills += (unsigned)nt;
     }
 #endif
-    // ---- (c) the steps, in visiting order: O(1) each
-    int c_next = (int)vq[0];
-    double coin_next = BC(c_next), prop_next = BP(c_next);
+    // ---- (c) the steps: O(1) each. Named parameters in the chain's substepper order, the components of a multi-dim parameter in its
+    // visiting order -- with one exception. When the components of a (large) multi-dim parameter never share a term (JBLOCK: the
+    // group means of a hierarchical model), every one of its decisions depends only on that component's own proposal, uniform and
+    // terms: any order gives the same draws. Its steps are then taken in INDEX order by all chains of the warp at once, so that every
+    // row access is contiguous (the visiting order is per chain: lanes would read 32 different rows), between the steps of the
+    // parameters the chain visits before it and those it visits after it.
+    {
+#if JBLOCK >= 0
+      int pos_b = 0;
+      for (int slot = 0; slot < JP; ++slot) if (((JP > 1) ? perm_get(a, perm, chain, slot) : 0) == JBLOCK) pos_b = slot;
 #pragma unroll 1
-    for (int i = 0; i < JD; ++i) {
-      const int c = c_next;
-      const double coin = coin_next, prop = prop_next;
-      if (i + 1 < JD) {                                         // the next step's operands are on their way while this one is evaluated
-        c_next = (int)vq[(unsigned long long)(i + 1) * ws];
-        coin_next = BC(c_next); prop_next = BP(c_next);
+      for (int part = 0; part < 3; ++part) {
+        if (part == 1) {
+          const int n_b = jp_ncomp(JBLOCK), off_b = jp_off(JBLOCK);
+          double coin_next = BC(off_b), prop_next = BP(off_b);
+#pragma unroll 1
+          for (int r = 0; r < n_b; ++r) {
+            const int c = off_b + r;
+            const double coin = coin_next, prop = prop_next;
+            if (r + 1 < n_b) { coin_next = BC(c + 1); prop_next = BP(c + 1); }
+            if (!wr || coin < 0.0) continue;
+            if (jit_step(c, prop, coin, wk, ws, sp, ss) && valid && A.adapting[c]) atomicAdd(&a.acc[(unsigned long long)c * C + chain], 1);
+          }
+          continue;
+        }
+        const int lo = part == 0 ? 0 : pos_b + 1, hi = part == 0 ? pos_b : JP;
+#else
+      {
+        const int lo = 0, hi = JP;
+#endif
+        int pos0 = 0;
+#pragma unroll 1
+        for (int slot = 0; slot < JP; ++slot) {
+          const int p = (JP > 1) ? perm_get(a, perm, chain, slot) : 0;
+          const int n_comp = jp_ncomp(p);
+          if (slot >= lo && slot < hi) {
+            int c_next = (int)vq[(unsigned long long)pos0 * ws];
+            double coin_next = BC(c_next), prop_next = BP(c_next);
+#pragma unroll 1
+            for (int r = 0; r < n_comp; ++r) {
+              const int c = c_next;
+              const double coin = coin_next, prop = prop_next;
+              if (r + 1 < n_comp) {                             // the next step's operands are on their way while this one is evaluated
+                c_next = (int)vq[(unsigned long long)(pos0 + r + 1) * ws];
+                coin_next = BC(c_next); prop_next = BP(c_next);
+              }
+              if (!wr || coin < 0.0) continue;                  // out of bounds: rejected without evaluation (mcmc.js:520-522)
+              if (jit_step(c, prop, coin, wk, ws, sp, ss) && valid && A.adapting[c])
+                atomicAdd(&a.acc[(unsigned long long)c * C + chain], 1);      // acceptance_count (mcmc.js:530); result unused: a RED
+            }
+          }
+          pos0 += n_comp;
+        }
       }
-      if (!wr || coin < 0.0) continue;                          // out of bounds: rejected without evaluation (mcmc.js:520-522)
-      if (jit_step(c, prop, coin, wk, ws, sp, ss) && valid && A.adapting[c])
-        atomicAdd(&a.acc[(unsigned long long)c * C + chain], 1);        // acceptance_count (mcmc.js:530); result unused: a RED
     }
   }
   if (valid) {

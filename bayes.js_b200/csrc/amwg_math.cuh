@@ -190,8 +190,9 @@ struct RandomStream {
   }
 };
 
-// rnorm -- mcmc.js:43-54 (Leva ratio-of-uniforms; two uniforms per trial)
-__device__ __forceinline__ double js_rnorm(RandomStream& g, uint64_t seed, uint64_t chain, double mean, double sd) {
+// rnorm -- mcmc.js:43-54 (Leva ratio-of-uniforms; two uniforms per trial). js_rnorm_ratio is the accepted v / u: the draw is
+// (v / u) * sd + mean, and a caller that does not have sd and mean at hand yet can finish it later with the same two operations.
+__device__ __forceinline__ double js_rnorm_ratio(RandomStream& g, uint64_t seed, uint64_t chain) {
   double u, v, x, y, q;
   do {
     double r;
@@ -201,7 +202,10 @@ __device__ __forceinline__ double js_rnorm(RandomStream& g, uint64_t seed, uint6
     y = fabs(v) + 0.386595;
     q = x * x + y * (0.19600 * y - 0.25472 * x);
   } while (q > 0.27597 && (q > 0.27846 || v * v > -4 * js_log(u) * u * u));
-  return (v / u) * sd + mean;
+  return v / u;
+}
+__device__ __forceinline__ double js_rnorm(RandomStream& g, uint64_t seed, uint64_t chain, double mean, double sd) {
+  return js_rnorm_ratio(g, seed, chain) * sd + mean;
 }
 
 }  // namespace amwg

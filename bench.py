@@ -110,7 +110,7 @@ class Config:
             self.flop_per_draw = 131072.0 * 3
             self.hbm_bytes_per_draw = 65 * 8 + 65 * (16 + 16 + 4) / 50.0
             self.flop_note = "SURVEY 8(d): minimal 64 x 1024 + 65536 = 131072 point-terms x 3 flop (the kernel caches each group's sum of squares: 65536 point-terms per sweep)"
-            self.cpu_draws, self.probe_sweeps, self.ks_chains, self.ks_sweeps = 3, 2, 512, 10
+            self.cpu_draws, self.probe_sweeps, self.ks_chains, self.ks_sweeps = 3, 1, 512, 5
         elif k == 5:
             K, n = 8, 1000000
             self.workload = "config 5: Poisson regression, 8 real coefs, N=1e6, 2^19 chains per GPU (2^22 on 8 GPUs)"
@@ -497,7 +497,11 @@ def run_ours(args):
                 v, sample = cpu_port_draws_per_sec(orc, cfg)
                 line["cpu_baseline"] = {"value": v, "unit": "draws/s", "cores": 1, "kind": "port", "sample": sample,
                                         "published_reference": "README.md:252: ~4e4 draws/s at N=1000 (author's machine, 2015)"}
-            if not args.no_probe:
+            # The probe steps `faithful` handles (the reference's arithmetic, term by term) on the FULL-SIZE data. On config 5 that is
+            # 8 x 1e6 interpreted point-terms per sweep for a single warp (minutes): asked for with --probe, recorded in profiles/.
+            # At N > 1 the other ranks would idle behind rank 0: the probe belongs to the single-GPU run of the same config.
+            want_probe = args.probe or (not args.no_probe and world == 1 and cfg.k != 5)
+            if want_probe:
                 line["parity_probe"] = parity_probe(cfg, mcmc, orc, chains_total, local_rank, seed)
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -517,6 +521,7 @@ def main():
     ap.add_argument("--burn", type=int, default=None, help="burn-in sweeps done in setup (untimed)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg and the parity probe")
     ap.add_argument("--no-probe", action="store_true", help="skip the in-run parity probe")
+    ap.add_argument("--probe", action="store_true", help="force the in-run parity probe (default: single-GPU runs of configs 2-4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -37,8 +37,8 @@ def test_hierarchical_model_classes_loops_and_streaming(pkg):
     # the 64 group means are ONE class (indices from tables), sigma's 64 plate terms are a loop, y (512 KB) streams through the ring
     assert "const int m = JMEM[c];" in src and "for (int j = 0; j < 63; ++j)" in src
     assert "#define JSTREAM 1" in src and "#define JN_SSTAT 64" in src and "#define JS_TOTAL 65536" in src
-    # a grid that fills 148 SMs evenly: 2^16 chains -> 293 CTAs of 224 threads, two per SM
-    assert "#define JTHREADS 224" in src and "#define JMINB 2" in src
+    # 2^16 chains: 512 CTAs of 128 threads, four per SM (measured faster than the better balanced 224 x 2)
+    assert "#define JTHREADS 128" in src and "#define JMINB 4" in src
 
 
 def test_expression_means_and_derived_quantities(pkg):
