@@ -200,7 +200,14 @@ def ncu_traffic(cfg_k: int, chains: int):
         if e and int(e.get("chains", -1)) == int(chains):
             return e, "profiles/ncu_traffic.json (%s)" % e.get("source", "?")
     except Exception:
-        pass
+        try:                                         # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+                cores = max(1, min(visible, int(quota + 0.999)))
+        except Exception:
+            pass
     return None, None
 
 
@@ -224,7 +231,15 @@ def run_reference(args):
     orc = graft.load_oracle()
     pkg = graft.load_package()
     cfg = Config(args.config, pkg.ld, pkg.mcmc)
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    visible = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cores, quota = visible, None
+    try:                                             # a container may see 128 CPUs and be allowed a fraction of them (cgroup v2 cpu.max)
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            quota = float(q) / float(per)
+            cores = max(1, min(visible, int(quota + 0.999)))
+    except Exception:
+        pass
     # per-thread work sized from a single-core probe so that one step is about 2.5 s
     t1 = orc.time_model(cfg.oracle_model, cfg.oracle_data, cfg.params, chains=1, burn=0, sample=cfg.cpu_draws)
     one_core = cfg.cpu_draws / t1
@@ -246,7 +261,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg.workload, "note": "CPU restatement of mcmc.js (Node unavailable); independent chains are the only parallelism the reference admits"},
             "cpu_baseline": {"value": value, "unit": "draws/s", "cores": cores, "kind": "port", "sample": sample,
-                             "single_core_draws_per_s": one_core, "parallel_efficiency": value / (one_core * cores)},
+                             "single_core_draws_per_s": one_core, "parallel_efficiency": value / (one_core * cores),
+                             "cpus_visible": visible, "cgroup_cpu_quota": quota},
             "e2e": {"value": value, "unit": "draws/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
