@@ -266,8 +266,25 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
     // terms: any order gives the same draws. Its steps are then taken in INDEX order by all chains of the warp at once, so that every
     // row access is contiguous (the visiting order is per chain: lanes would read 32 different rows), between the steps of the
     // parameters the chain visits before it and those it visits after it.
+#if JBLOCK < 0
     {
-#if JBLOCK >= 0
+      int c_next = (int)vq[0];
+      double coin_next = BC(c_next), prop_next = BP(c_next);
+#pragma unroll 1
+      for (int i = 0; i < JD; ++i) {
+        const int c = c_next;
+        const double coin = coin_next, prop = prop_next;
+        if (i + 1 < JD) {                                       // the next step's operands are on their way while this one is evaluated
+          c_next = (int)vq[(unsigned long long)(i + 1) * ws];
+          coin_next = BC(c_next); prop_next = BP(c_next);
+        }
+        if (!wr || coin < 0.0) continue;                        // out of bounds: rejected without evaluation (mcmc.js:520-522)
+        if (jit_step(c, prop, coin, wk, ws, sp, ss) && valid && A.adapting[c])
+          atomicAdd(&a.acc[(unsigned long long)c * C + chain], 1);        // acceptance_count (mcmc.js:530); result unused: a RED
+      }
+    }
+#else
+    {
       int pos_b = 0;
       for (int slot = 0; slot < JP; ++slot) if (((JP > 1) ? perm_get(a, perm, chain, slot) : 0) == JBLOCK) pos_b = slot;
 #pragma unroll 1
@@ -286,10 +303,6 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
           continue;
         }
         const int lo = part == 0 ? 0 : pos_b + 1, hi = part == 0 ? pos_b : JP;
-#else
-      {
-        const int lo = 0, hi = JP;
-#endif
         int pos0 = 0;
 #pragma unroll 1
         for (int slot = 0; slot < JP; ++slot) {
@@ -315,6 +328,7 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
         }
       }
     }
+#endif
   }
   if (valid) {
     a.rng_n[chain] = g.n;
