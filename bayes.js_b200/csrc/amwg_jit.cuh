@@ -735,6 +735,7 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
   int nacc = 4;
   if (const char* e = getenv("AMWG_JIT_NACC")) { int v = atoi(e); if (v == 4 || v == 8) nacc = v; }
   pre << "#define AMWG_NACC " << nacc << "\n";
+
   src.prelude = pre.str();
   funcs << tables.str() << step.str() << extra.str() << dfun.str() << "}  // namespace amwg\n";
   src.generated = funcs.str();
