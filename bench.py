@@ -21,7 +21,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -143,39 +142,57 @@ class Config:
         self.n_entries = sum(int(np.prod(p.get("dim", [1]))) for p in self.params.values())
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region: one `nvidia-smi -lms 100` process started before the region and
+    stopped after it (a fresh nvidia-smi per sample takes longer than a whole timed step)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.index, self.proc = index, None
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([f.strip() for f in out.split(",")])
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=3)
-        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+                out, _ = self.proc.communicate(timeout=5)
+                rows = [[f.strip() for f in ln.split(",")] for ln in out.strip().splitlines() if ln.strip()]
+            except Exception:
+                try:
+                    self.proc.kill()
+                except Exception:
+                    pass
+        if not rows:                                  # the region was shorter than nvidia-smi's start-up: one sample right after it
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=10).stdout.strip()
+                rows = [[f.strip() for f in out.split(",")]] if out else []
+            except Exception:
+                rows = []
+
+        def num(v):
+            try:
+                return float(v)
+            except ValueError:
+                return None
+        sm = [num(r[0]) for r in rows if r and num(r[0]) is not None]
+        mx = [num(r[1]) for r in rows if len(r) > 1 and num(r[1]) is not None]
+        pw = [num(r[2]) for r in rows if len(r) > 2 and num(r[2]) is not None]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(self.rows)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(rows)}
 
 
 def measured_peaks():
@@ -382,6 +399,7 @@ def run_ours(args):
     clocks = ClockSampler(local_rank) if rank == 0 else None
     if clocks:
         clocks.start()
+        time.sleep(0.3)                               # let nvidia-smi come up: its samples then fall inside the timed region
     launches0 = sampler.kernel_launches()
     barrier()
     t0 = time.perf_counter()
