@@ -313,6 +313,16 @@
   };
   AmwgSampler.prototype.burn = function (n) { native.burn(this.model.handle, Math.floor(n)); };
   AmwgSampler.prototype.sample = function (n) { return this.model.sample(n, this.thinning_interval, this.monitored_params); };
+  // Not in the reference: sample(n) without the reshaping into nested arrays -- for millions of chains the nested form is impractical.
+  // -> {data: flat array (Float64Array under Node) laid out [row][entry][chain], shape: [rows, entries, chains], entries: [{name, index}]}
+  AmwgSampler.prototype.sample_raw = function (n) {
+    var m = this.model, monitored = this.monitored_params === null ? m.state_keys() : this.monitored_params, entries = [], labels = [], i, j, e, thin, rows;
+    for (i = 0; i < monitored.length; i++) { e = m.entries(monitored[i]); for (j = 0; j < e.length; j++) { entries.push(e[j]); labels.push({name: monitored[i], index: j}); } }
+    thin = Math.abs(Math.floor(this.thinning_interval));
+    if (!(thin >= 1)) { throw "sample_raw needs thin >= 1"; }
+    rows = n <= 0 ? 0 : Math.ceil(Math.floor(n) / thin);
+    return {data: native.sample(m.handle, Math.floor(n), thin, entries), shape: [rows, entries.length, m.n_chains], entries: labels};
+  };
   AmwgSampler.prototype.step = function () { this.burn(1); return this.model.state(); };
   AmwgSampler.prototype.state = function () { return this.model.state(); };
   AmwgSampler.prototype.log_post = function () { var lp = native.get_log_post(this.model.handle); return this.n_chains === 1 ? lp[0] : lp; };
