@@ -139,6 +139,7 @@ struct Plan {                                                  // shared-memory 
 };
 
 struct Source {
+  bool full = false;                                           // amwg_jit_full_kernel.cuh instead of amwg_jit_kernel.cuh
   std::string generated;                                       // "amwg_jit_generated.inc"
   std::string prelude;                                         // the #defines and tables that precede the skeleton
   Plan plan;
@@ -153,6 +154,7 @@ struct Emitter {
   std::ostringstream os;
   std::map<std::string, std::string> cse;
   std::vector<std::string> stk;
+  std::vector<std::map<std::string, std::string>> scopes;     // values named inside a generated loop are not visible after it
   int nv = 0;
   std::string tmp(const std::string& rhs) {
     auto it = cse.find(rhs);
@@ -171,8 +173,10 @@ struct Inst {
   std::vector<Insn> ins;
   int moved = -1;                                              // the component this instance steps (-1: none, e.g. stat / derived code)
 };
+struct Plan;
 struct GenCtx {
   const amwg_model* md = nullptr;
+  const Plan* plan = nullptr;                                  // shared-memory offsets of the resident columns (full-program code)
   const std::vector<double>* consts = nullptr;                 // constants with the device-folded values filled in
   std::ostringstream* tables = nullptr;                        // where the integer tables are emitted
   int* table_counter = nullptr;
@@ -200,13 +204,14 @@ struct GenCtx {
   }
 };
 
-enum CompContext { CTX_STEP, CTX_STAT, CTX_DERIVED };
+enum CompContext { CTX_STEP, CTX_STAT, CTX_DERIVED, CTX_FULL };
 struct Term { std::string tid, val; };
 
 // the value of state component `idx` as an instance's code sees it
 static std::string comp_ref(const std::vector<Inst>& inst, const std::vector<int>& idxs, const std::string& idx, bool same, CompContext cx) {
   if (cx == CTX_STAT) return "BP(" + idx + ")";               // the whole proposal vector (amwg.h stat_prog)
   if (cx == CTX_DERIVED) return "ST(" + idx + ")";
+  if (cx == CTX_FULL) return "CM(" + idx + ")";               // full-program evaluation: the moved component is a run-time value
   bool all_moved = true, none_moved = true;
   for (size_t m = 0; m < inst.size(); ++m) { all_moved = all_moved && idxs[m] == inst[m].moved; none_moved = none_moved && idxs[m] != inst[m].moved; }
   if (all_moved) return "prop";
@@ -341,6 +346,58 @@ static bool emit_range(const GenCtx& gc, const std::vector<Inst>& inst, size_t i
         r = "(" + nn + " * (JNORM_C0 - " + lsd + ") - " + x + " / " + k2 + ")";
         break;
       }
+      case AMWG_OP_DATA_I: case AMWG_OP_COMP_I: {             // inside a generated loop: columns[a][off + stride * i_]
+        if (cx != CTX_FULL || M != 1 || !gc.plan) { why = "plate-indexed data outside a full-program loop"; return false; }
+        if (in.a >= md->n_columns || gc.plan->col_smem_off[in.a] < 0) { why = "a looped column is not resident"; return false; }
+        std::string at = "LD(" + std::to_string(gc.plan->col_smem_off[in.a] + 8 * in.extra[0]) + "u + " + std::to_string(8 * in.extra[1]) + "u * (unsigned)i_)";
+        r = in.op == AMWG_OP_DATA_I ? at : "CM(" + std::to_string(in.extra[2]) + " + (int)" + at + ")";
+        break;
+      }
+      case AMWG_OP_ACC: {
+        if (cx != CTX_FULL) { why = "ACC outside a full-program evaluation"; return false; }
+        if (em.stk.empty()) { why = "stack underflow"; return false; }
+        em.os << "    lp = lp + " << em.stk.back() << ";\n"; em.stk.pop_back();
+        has_r = false;
+        break;
+      }
+      case AMWG_OP_LOOP_BEGIN: {
+        if (cx != CTX_FULL) { why = "loop outside a full-program evaluation"; return false; }
+        if (in.a >= md->n_plates) { why = "plate index out of range"; return false; }
+        em.scopes.push_back(em.cse);
+        em.os << "    for (int i_ = 0; i_ < " << md->plates[in.a].n << "; ++i_) {\n";
+        has_r = false;
+        break;
+      }
+      case AMWG_OP_LOOP_END: {
+        if (cx != CTX_FULL || em.scopes.empty() || em.stk.empty()) { why = "malformed loop"; return false; }
+        em.os << "    lp = lp + " << em.stk.back() << ";\n    }\n"; em.stk.pop_back();
+        em.cse = em.scopes.back(); em.scopes.pop_back();
+        has_r = false;
+        break;
+      }
+      case AMWG_OP_PLATE: {
+        if (cx != CTX_FULL || !gc.plan) { why = "plate outside a full-program evaluation"; return false; }
+        const amwg_plate& pq = md->plates[in.a];
+        const int c0 = pq.col[0];
+        if (c0 < 0 || c0 >= md->n_columns || gc.plan->col_smem_off[c0] < 0) { why = "a plate's column is not resident"; return false; }
+        const std::string boff = std::to_string(gc.plan->col_smem_off[c0] + 8 * pq.iparam[2]);
+        if (pq.kind == AMWG_PLATE_NORM_IID) {                   // operands: A = mean, B = sd
+          em.os << "    lp = lp + jit_norm_factorised(" << lit((double)pq.n) << ", sum_sq_dev(reinterpret_cast<const double*>(smem + " << boff << "), smem_u32(smem) + "
+                << boff << "u, " << pq.n << ", " << x << "), " << y << ");\n";
+        } else if (pq.kind == AMWG_PLATE_BERN_IID) {
+          em.os << "    lp = jit_plate_bern(smem_u32(smem) + " << boff << "u, " << pq.n << ", " << x << ", lp);\n";
+        } else if (pq.kind == AMWG_PLATE_NORM_GROUPED) {        // operand A = sd; points sorted by group, starts in col[1]
+          const int c1 = pq.col[1];
+          if (c1 < 0 || c1 >= md->n_columns || gc.plan->col_smem_off[c1] < 0) { why = "a plate's column is not resident"; return false; }
+          const std::string soff = std::to_string(gc.plan->col_smem_off[c1]), coff = std::to_string(gc.plan->col_smem_off[c0]);
+          em.os << "    {\n      double S_ = 0.0;\n      for (int j_ = 0; j_ < " << pq.iparam[1] << "; ++j_) {\n"
+                << "        const int a_ = (int)LD(" << soff << "u + 8u * (unsigned)j_) + " << pq.iparam[2] << ", b_ = (int)LD(" << soff << "u + 8u * (unsigned)(j_ + 1)) + " << pq.iparam[2] << ";\n"
+                << "        S_ = S_ + sum_sq_dev(reinterpret_cast<const double*>(smem + " << coff << " + 8 * a_), smem_u32(smem) + " << coff << "u + 8u * (unsigned)a_, b_ - a_, CM(" << pq.iparam[0] << " + j_));\n"
+                << "      }\n      lp = lp + jit_norm_factorised(" << lit((double)pq.n) << ", S_, " << x << ");\n    }\n";
+        } else { why = "this plate kind is not specialised"; return false; }
+        has_r = false;
+        break;
+      }
       case AMWG_OP_STORE: {
         if (cx != CTX_DERIVED) { why = "STORE outside a derived-quantity program"; return false; }
         if (em.stk.empty()) { why = "stack underflow"; return false; }
@@ -353,7 +410,9 @@ static bool emit_range(const GenCtx& gc, const std::vector<Inst>& inst, size_t i
     }
     if (!has_r) continue;
     std::string name = em.tmp(r);                               // every value gets a name; identical right-hand sides are shared
-    if (in.acc) {
+    if (in.acc && cx == CTX_FULL) {
+      em.os << "    lp = lp + " << name << ";\n";              // the sum is formed in program order, like the JS `log_post += ...`
+    } else if (in.acc) {
       if (!in.store) { why = "a term of the sum is not cached"; return false; }
       terms.push_back(Term{gc.field(gather(i, [](const Insn& q) { return q.term; }), ix), name});
     } else {
@@ -447,7 +506,63 @@ static std::string signature(const std::vector<Insn>& prog) {
   return s;
 }
 
-struct Reject { std::string why; };
+// Launch shape: CTA size and resident CTAs per SM such that the chains spread evenly over the SMs; the per-chain working set
+// (`per_thread` bytes) goes to shared memory when it is small. `off`: shared memory already planned (columns, ring).
+static std::string choose_shape(Plan& pl, unsigned off, size_t per_thread, unsigned long long n_chains, int sm_count) {
+  const unsigned base = off;
+  int best_t = 0, best_r = 1, best_ws = 0;
+  double best_eff = -1.0;
+  const int cands[] = {128, 64, 96, 160, 192, 224, 256};
+  int forced_t = 0;
+  if (const char* e = getenv("AMWG_JIT_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) forced_t = t; }
+  for (int t : cands) {
+    if (forced_t) t = forced_t;
+    const size_t need = pad16(per_thread * (size_t)t);
+    const int ws_smem = need <= kJitWsSmemLimit;
+    const unsigned smem = std::max((unsigned)(pad16(base) + (ws_smem ? need : 0)), 16u);
+    int r_max = (int)std::min<unsigned>(std::min<unsigned>((227u * 1024u) / (smem + 1024u), 2048u / (unsigned)t), 8u);
+    if (r_max < 1) continue;
+    const double ctas = std::ceil((double)n_chains / t);
+    const double cap = (double)sm_count * r_max;
+    double eff; int r_need;
+    if (ctas <= cap) { const double per_sm = std::ceil(ctas / sm_count); eff = ((double)n_chains / sm_count) / (per_sm * t); r_need = (int)per_sm; }
+    else { eff = ctas / (std::ceil(ctas / cap) * cap) * ((double)n_chains / (ctas * t)); r_need = r_max; }
+    // 128-thread CTAs are the default; another size has to fill the SMs a good deal more evenly to win (config 4 at 2^16 chains:
+    // 224 x 2 CTAs/SM is 14 % better balanced than 128 x 4 and measured 6 % SLOWER -- more, smaller CTAs overlap their phases)
+    if (eff > best_eff + (best_t == 0 ? 0.0 : 0.15)) { best_eff = eff; best_t = t; best_r = r_need; best_ws = ws_smem; }
+    if (forced_t) break;
+  }
+  if (!best_t) return "no launch shape fits";
+  pl.threads = best_t;
+  if (best_ws) { pl.ws_smem = 1; pl.ws_off = (int)pad16(off); off = (unsigned)(pad16(off) + pad16(per_thread * (size_t)best_t)); }
+  pl.smem_bytes = std::max(off, 16u);
+  pl.minblocks = std::max(1, best_r);
+  if (const char* e = getenv("AMWG_JIT_MINBLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 16) pl.minblocks = v; }
+  return "";
+}
+
+
+static void emit_param_tables(std::ostringstream& tables, const amwg_model* md) {
+  const int P = md->n_params;
+  auto ptab = [&](const char* ty, const char* name, auto get) {
+    tables << "__constant__ " << ty << " " << name << "[" << P << "] = {";
+    for (int p = 0; p < P; ++p) tables << (p ? "," : "") << get(md->params[p]);
+    tables << "};\n";
+  };
+  ptab("int", "JP_TYPE", [](const amwg_param& p) { return istr(p.type); });
+  ptab("int", "JP_NCOMP", [](const amwg_param& p) { return istr(p.n_comp); });
+  ptab("int", "JP_DIM0", [](const amwg_param& p) { return istr(p.dim0); });
+  ptab("int", "JP_OFF", [](const amwg_param& p) { return istr(p.comp_offset); });
+  ptab("long long", "JP_LOWER", [](const amwg_param& p) { return bits(p.lower); });
+  ptab("long long", "JP_UPPER", [](const amwg_param& p) { return bits(p.upper); });
+  tables << "__device__ __forceinline__ int jp_type(int p) { return JP_TYPE[p]; }\n"
+            "__device__ __forceinline__ int jp_ncomp(int p) { return JP_NCOMP[p]; }\n"
+            "__device__ __forceinline__ int jp_dim0(int p) { return JP_DIM0[p]; }\n"
+            "__device__ __forceinline__ int jp_off(int p) { return JP_OFF[p]; }\n"
+            "__device__ __forceinline__ double jp_lower(int p) { return __longlong_as_double(JP_LOWER[p]); }\n"
+            "__device__ __forceinline__ double jp_upper(int p) { return __longlong_as_double(JP_UPPER[p]); }\n";
+}
+
 
 // Build the specialised translation unit for `md`. Returns "" and fills `src` on success, else the reason it does not apply.
 static std::string build_source(const amwg_model* md, const std::vector<double>& consts, unsigned long long n_chains, int sm_count,
@@ -531,39 +646,10 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
     pl.ring_off = (int)off;
     off += (unsigned)(pl.ring_stages * pl.ring_tile * 8);
   }
-  // launch shape: CTA size and resident CTAs per SM such that the chains spread evenly over the SMs; the working set goes to shared
-  // memory when it is small
   {
     const size_t per_thread = sizeof(double) * (size_t)(2 * NT + 3 * D) + sizeof(unsigned short) * (size_t)D;
-    const unsigned base = off;
-    int best_t = 0, best_r = 1, best_ws = 0;
-    double best_eff = -1.0;
-    const int cands[] = {128, 64, 96, 160, 192, 224, 256};
-    int forced_t = 0;
-    if (const char* e = getenv("AMWG_JIT_THREADS")) { int t = atoi(e); if (t >= 32 && t <= 1024 && t % 32 == 0) forced_t = t; }
-    for (int t : cands) {
-      if (forced_t) t = forced_t;
-      const size_t need = pad16(per_thread * (size_t)t);
-      const int ws_smem = need <= kJitWsSmemLimit;
-      const unsigned smem = std::max((unsigned)(pad16(base) + (ws_smem ? need : 0)), 16u);
-      int r_max = (int)std::min<unsigned>(std::min<unsigned>((227u * 1024u) / (smem + 1024u), 2048u / (unsigned)t), 8u);
-      if (r_max < 1) continue;
-      const double ctas = std::ceil((double)n_chains / t);
-      const double cap = (double)sm_count * r_max;
-      double eff; int r_need;
-      if (ctas <= cap) { const double per_sm = std::ceil(ctas / sm_count); eff = ((double)n_chains / sm_count) / (per_sm * t); r_need = (int)per_sm; }
-      else { eff = ctas / (std::ceil(ctas / cap) * cap) * ((double)n_chains / (ctas * t)); r_need = r_max; }
-      // 128-thread CTAs are the default; another size has to fill the SMs a good deal more evenly to win (config 4 at 2^16 chains:
-      // 224 x 2 CTAs/SM is 14 % better balanced than 128 x 4 and measured 6 % SLOWER -- more, smaller CTAs overlap their phases)
-      if (eff > best_eff + (best_t == 0 ? 0.0 : 0.15)) { best_eff = eff; best_t = t; best_r = r_need; best_ws = ws_smem; }
-      if (forced_t) break;
-    }
-    if (!best_t) return "no launch shape fits";
-    pl.threads = best_t;
-    if (best_ws) { pl.ws_smem = 1; pl.ws_off = (int)pad16(off); off = (unsigned)(pad16(off) + pad16(per_thread * (size_t)best_t)); }
-    pl.smem_bytes = std::max(off, 16u);
-    pl.minblocks = std::max(1, best_r);
-    if (const char* e = getenv("AMWG_JIT_MINBLOCKS")) { int v = atoi(e); if (v >= 1 && v <= 16) pl.minblocks = v; }
+    std::string e = choose_shape(pl, off, per_thread, n_chains, sm_count);
+    if (!e.empty()) return e;
   }
 
   // ---- component programs -> classes
@@ -669,24 +755,7 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
     for (int i = 0; i < md->n_consts; ++i) tables << (i ? "," : "") << bits(consts[i]);
     if (md->n_consts == 0) tables << "0LL";
     tables << "};\n#define KC(i) __longlong_as_double(KCB[i])\n";
-    // parameters (mcmc.js:357-403 completed)
-    auto ptab = [&](const char* ty, const char* name, auto get) {
-      tables << "__constant__ " << ty << " " << name << "[" << P << "] = {";
-      for (int p = 0; p < P; ++p) tables << (p ? "," : "") << get(md->params[p]);
-      tables << "};\n";
-    };
-    ptab("int", "JP_TYPE", [](const amwg_param& p) { return istr(p.type); });
-    ptab("int", "JP_NCOMP", [](const amwg_param& p) { return istr(p.n_comp); });
-    ptab("int", "JP_DIM0", [](const amwg_param& p) { return istr(p.dim0); });
-    ptab("int", "JP_OFF", [](const amwg_param& p) { return istr(p.comp_offset); });
-    ptab("long long", "JP_LOWER", [](const amwg_param& p) { return bits(p.lower); });
-    ptab("long long", "JP_UPPER", [](const amwg_param& p) { return bits(p.upper); });
-    tables << "__device__ __forceinline__ int jp_type(int p) { return JP_TYPE[p]; }\n"
-              "__device__ __forceinline__ int jp_ncomp(int p) { return JP_NCOMP[p]; }\n"
-              "__device__ __forceinline__ int jp_dim0(int p) { return JP_DIM0[p]; }\n"
-              "__device__ __forceinline__ int jp_off(int p) { return JP_OFF[p]; }\n"
-              "__device__ __forceinline__ double jp_lower(int p) { return __longlong_as_double(JP_LOWER[p]); }\n"
-              "__device__ __forceinline__ double jp_upper(int p) { return __longlong_as_double(JP_UPPER[p]); }\n";
+    emit_param_tables(tables, md);                              // parameters (mcmc.js:357-403 completed)
     // resident columns and the simple statistics over them
     std::vector<long long> a, b, c2, d;
     for (int k = 0; k < pl.n_res; ++k) { a.push_back(pl.res_off[k]); b.push_back(pl.res_col[k]); c2.push_back(pl.res_bytes[k]); }
@@ -742,6 +811,133 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
   return "";
 }
 
+
+// The specialised form of the full-program sweep (amwg_jit_full_kernel.cuh): for models that evaluate all of log_post at every step
+// (no term cache, no statistics): the program -- per configuration of the binary components, if it has variants -- printed as
+// straight-line code, bit-identical to what the interpreter computes. Returns "" and fills `src`, else why it does not apply.
+static std::string build_source_full(const amwg_model* md, const std::vector<double>& consts, unsigned long long n_chains, int sm_count,
+                                     double norm_c0, Source& src) {
+  if (md->comp_prog && md->n_terms > 0) return "the model steps with a term cache";
+  const int D = md->n_comp, P = md->n_params;
+  if (D > 65535 || P > 255) return "too many components / parameters";
+  int max_dim0 = 1;
+  for (int p = 0; p < P; ++p) if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, md->params[p].dim0);
+  std::string err;
+  Plan& pl = src.plan;
+  pl = Plan();
+  pl.col_smem_off.assign(md->n_columns, -1);
+  unsigned off = 0;
+  for (int c = 0; c < md->n_columns; ++c) {                     // every column resident, or the model stays on the interpreter
+    const unsigned bytes = pad16(std::max<size_t>(sizeof(double) * (size_t)md->columns[c].n, 16));
+    if (off + bytes > kResidentBudget) return "the data does not fit in shared memory";
+    pl.col_smem_off[c] = (int)off; pl.res_col.push_back(c); pl.res_off.push_back((int)off); pl.res_bytes.push_back((int)bytes);
+    off += bytes;
+  }
+  pl.n_res = (int)pl.res_col.size();
+  { std::string e = choose_shape(pl, off, sizeof(double) * (size_t)D, n_chains, sm_count); if (!e.empty()) return e; }
+
+  std::ostringstream tables, funcs;
+  int table_counter = 0, total_insns = 0;
+  GenCtx gc;
+  gc.md = md; gc.consts = &consts; gc.tables = &tables; gc.table_counter = &table_counter; gc.plan = &pl;
+  // the distinct programs: one, or one per configuration of the program-selecting binary components
+  const int n_var = md->n_variant_comps ? (1 << md->n_variant_comps) : 1;
+  auto emit_program = [&](int pc, const std::string& name, bool derived) -> std::string {
+    Inst it;
+    if (!decode_program(md, pc, it.ins, nullptr, err)) return "program: " + err;
+    total_insns += (int)it.ins.size();
+    if (total_insns > kMaxGeneratedInsns) return "the programs are too long to specialise";
+    std::vector<Inst> inst{it};
+    Emitter em;
+    std::vector<Term> terms; std::vector<std::string> cands; std::vector<std::pair<int, std::string>> der;
+    std::string why;
+    if (!emit_range(gc, inst, 0, it.ins.size(), "m", derived ? CTX_DERIVED : CTX_FULL, em, terms, cands, der, why)) return why;
+    if (!em.scopes.empty()) return "unterminated loop";
+    if (derived) {
+      funcs << "__device__ __forceinline__ void " << name << "(unsigned char* smem, const double* __restrict__ sp, const unsigned long long ss, double* der) {\n" << em.os.str();
+      for (auto& d : der) { if (d.first < 0 || d.first >= md->n_derived) return std::string("derived index out of range"); funcs << "    der[" << d.first << "] = " << d.second << ";\n"; }
+      funcs << "  (void)smem;\n}\n";
+    } else {
+      funcs << "__device__ " << (it.ins.size() > 600 ? "__noinline__" : "__forceinline__") << " double " << name
+            << "(unsigned char* smem, const double* __restrict__ sp, const unsigned long long ss, const int moved, const double val) {\n    double lp = 0.0;\n"
+            << em.os.str() << "    (void)smem;\n    return lp;\n}\n";
+    }
+    return "";
+  };
+  funcs << "namespace amwg {\n#define LD(o) lds_f64_sa(smem_u32(smem) + (o))\n";
+  std::ostringstream body;
+  for (int v = 0; v < n_var; ++v) {
+    const int pc = md->n_variant_comps ? md->variant_logpost[v] : md->logpost_prog;
+    std::string e = emit_program(pc, "jit_prog_" + std::to_string(v), false);
+    if (!e.empty()) return "log_post: " + e;
+  }
+  if (md->n_derived > 0)
+    for (int v = 0; v < n_var; ++v) {
+      const int pc = md->n_variant_comps ? (md->variant_derived ? md->variant_derived[v] : -1) : md->derived_prog;
+      if (pc < 0) return "a configuration has no derived program";
+      std::string e = emit_program(pc, "jit_der_" + std::to_string(v), true);
+      if (!e.empty()) return "derived: " + e;
+    }
+  // which recorded configuration of the binary components applies (amwg.h variant_*): bit k set when component variant_comps[k] != 0
+  auto variant_expr = [&](bool with_moved) {
+    std::string e = "0";
+    for (int k = 0; k < md->n_variant_comps; ++k) {
+      const std::string c = std::to_string(md->variant_comps[k]);
+      e += " | ((" + (with_moved ? "CM(" + c + ")" : "ST(" + c + ")") + " != 0.0) ? " + std::to_string(1 << k) + " : 0)";
+    }
+    return e;
+  };
+  funcs << tables.str();
+  funcs << "__device__ __forceinline__ double jit_logpost(unsigned char* smem, const double* __restrict__ sp, const unsigned long long ss, const int moved, const double val) {\n";
+  if (n_var == 1) funcs << "  return jit_prog_0(smem, sp, ss, moved, val);\n";
+  else {
+    funcs << "  switch (" << variant_expr(true) << ") {\n";
+    for (int v = 0; v < n_var; ++v) funcs << "    case " << v << ": return jit_prog_" << v << "(smem, sp, ss, moved, val);\n";
+    funcs << "  }\n  return CUDART_NAN;\n";
+  }
+  funcs << "}\n";
+  if (md->n_derived > 0) {
+    funcs << "__device__ __forceinline__ void jit_derived(unsigned char* smem, const double* __restrict__ sp, const unsigned long long ss, double* der) {\n";
+    if (n_var == 1) funcs << "  jit_der_0(smem, sp, ss, der);\n";
+    else {
+      funcs << "  switch (" << variant_expr(false) << ") {\n";
+      for (int v = 0; v < n_var; ++v) funcs << "    case " << v << ": jit_der_" << v << "(smem, sp, ss, der); break;\n";
+      funcs << "  }\n";
+    }
+    funcs << "}\n";
+  }
+  // tables the skeleton reads
+  std::ostringstream t2;
+  emit_param_tables(t2, md);
+  auto int_table = [&](const char* qual, const char* name, const std::vector<long long>& v) {
+    t2 << qual << " " << name << "[" << std::max<size_t>(v.size(), 1) << "] = {";
+    for (size_t i = 0; i < v.size(); ++i) t2 << (i ? "," : "") << v[i];
+    if (v.empty()) t2 << "0";
+    t2 << "};\n";
+  };
+  std::vector<long long> a1, b1, c1;
+  for (int k = 0; k < pl.n_res; ++k) { a1.push_back(pl.res_off[k]); b1.push_back(pl.res_col[k]); c1.push_back(pl.res_bytes[k]); }
+  int_table("__constant__ unsigned", "JRES_OFF", a1); int_table("__constant__ int", "JRES_COL", b1); int_table("__constant__ unsigned", "JRES_BYTES", c1);
+  t2 << "__device__ const long long KCB[" << std::max(md->n_consts, 1) << "] = {";
+  for (int i = 0; i < md->n_consts; ++i) t2 << (i ? "," : "") << bits(consts[i]);
+  if (md->n_consts == 0) t2 << "0LL";
+  t2 << "};\n#define KC(i) __longlong_as_double(KCB[i])\n";
+  unsigned long long res_total = 0;
+  for (int k = 0; k < pl.n_res; ++k) res_total += (unsigned)pl.res_bytes[k];
+  std::ostringstream pre;
+  pre << "#define JFULL 1\n#define JD " << D << "\n#define JP " << P << "\n#define JTHREADS " << pl.threads << "\n#define JMINB " << pl.minblocks
+      << "\n#define JWS_SMEM " << pl.ws_smem << "\n#define JWS_OFF " << pl.ws_off << "\n#define JN_DERIVED " << md->n_derived << "\n#define JMAX_DIM0 " << max_dim0
+      << "\n#define JMAXCOL " << kMaxColumns << "\n#define JN_RES " << pl.n_res << "\n#define JRES_TOTAL_BYTES " << res_total << "u\n#define JNORM_C0 " << lit(norm_c0)
+      << "\n#define AMWG_REAL 0\n#define AMWG_INT 1\n#define AMWG_BINARY 2\n#define AMWG_NACC 4\n";
+  src.prelude = pre.str();
+  // the order inside the generated header: tables the programs use, parameter tables, programs
+  std::string f = funcs.str();
+  const std::string ns = "namespace amwg {\n#define LD(o) lds_f64_sa(smem_u32(smem) + (o))\n";
+  src.generated = ns + t2.str() + f.substr(ns.size()) + "}  // namespace amwg\n";
+  src.full = true;
+  return "";
+}
+
 // ---- NVRTC (loaded at run time) ---------------------------------------------------------------------------------------------------
 typedef int nvrtcResult_t;
 typedef struct _nvrtcProgram* nvrtcProgram_t;
@@ -786,7 +982,8 @@ static Nvrtc* nvrtc() {
 #include "amwg_embedded.inc"
 
 static std::string main_source(const Source& s) {
-  return s.prelude + "#include \"amwg_math.cuh\"\n#include \"amwg_ld.cuh\"\n#include \"amwg_tma.cuh\"\n#include \"amwg_jit_kernel.cuh\"\n";
+  return s.prelude + "#include \"amwg_math.cuh\"\n#include \"amwg_ld.cuh\"\n#include \"amwg_tma.cuh\"\n#include \"" +
+         (s.full ? "amwg_jit_full_kernel.cuh" : "amwg_jit_kernel.cuh") + "\"\n";
 }
 
 // Compile to a cubin for sm_100a. Returns "" on success.
@@ -794,10 +991,10 @@ static std::string compile(const Source& s, std::vector<char>& cubin, std::strin
   Nvrtc* nv = nvrtc();
   if (!nv->error.empty()) return nv->error;
   const std::string main_src = main_source(s);
-  const char* headers[] = {kSrcMath, kSrcLd, kSrcTma, kSrcJitKernel, s.generated.c_str()};
-  const char* names[] = {"amwg_math.cuh", "amwg_ld.cuh", "amwg_tma.cuh", "amwg_jit_kernel.cuh", "amwg_jit_generated.inc"};
+  const char* headers[] = {kSrcMath, kSrcLd, kSrcTma, kSrcJitKernel, kSrcJitFullKernel, s.generated.c_str()};
+  const char* names[] = {"amwg_math.cuh", "amwg_ld.cuh", "amwg_tma.cuh", "amwg_jit_kernel.cuh", "amwg_jit_full_kernel.cuh", "amwg_jit_generated.inc"};
   nvrtcProgram_t prog = nullptr;
-  nvrtcResult_t rc = nv->CreateProgram(&prog, main_src.c_str(), "amwg_jit_model.cu", 5, headers, names);
+  nvrtcResult_t rc = nv->CreateProgram(&prog, main_src.c_str(), "amwg_jit_model.cu", 6, headers, names);
   if (rc != 0) return std::string("nvrtcCreateProgram: ") + nv->GetErrorString(rc);
   const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "--fmad=false", "-lineinfo", "-DAMWG_JIT=1", "--ptxas-options=-v"};
   rc = nv->CompileProgram(prog, 6, opts);
@@ -860,7 +1057,7 @@ static void write_file(const std::string& dir, const std::string& path, const st
 }
 
 static std::string get_cubin(const Source& s, std::vector<char>& cubin, std::string& log, bool* from_cache) {
-  const unsigned long long h = fnv1a(s.generated, fnv1a(s.prelude, fnv1a(kSrcJitKernel, fnv1a(kSrcTma, fnv1a(kSrcMath, fnv1a(kSrcLd))))));
+  const unsigned long long h = fnv1a(s.generated, fnv1a(s.prelude, fnv1a(kSrcJitKernel, fnv1a(kSrcJitFullKernel, fnv1a(kSrcTma, fnv1a(kSrcMath, fnv1a(kSrcLd)))))));
   char name[64];
   snprintf(name, sizeof name, "/amwg_%016llx.cubin", h);
   const std::string dir = cache_dir(), path = dir + name;

@@ -1350,7 +1350,8 @@ static void try_jit(amwg_sampler* s, const amwg_model* md) {
   int want = -1;                                        // -1: when it pays (many chains), 0: never, 1: whenever the model is eligible
   if (const char* e = getenv("AMWG_JIT")) want = atoi(e);
   if (want == 0) { s->jit_note = "disabled (AMWG_JIT=0)"; return; }
-  if (s->m.stat_prog < 0) { s->jit_note = "the model does not run the statistics sweep"; return; }
+  const bool stat_model = s->m.stat_prog >= 0;
+  if (!stat_model && s->m.n_terms > 0) { s->jit_note = "the model steps with a term cache (interpreter kernels)"; return; }
   if (want < 0 && s->a.C < 4096) { s->jit_note = "fewer than 4096 chains: the interpreter kernels start faster than a compilation"; return; }
   std::vector<double> consts((size_t)std::max(md->n_consts, 1), 0.0);
   if (md->n_consts > 0 &&
@@ -1362,7 +1363,8 @@ static void try_jit(amwg_sampler* s, const amwg_model* md) {
   cudaDeviceProp prop{};
   if (cudaGetDeviceProperties(&prop, s->device) != cudaSuccess) { s->jit_note = "cudaGetDeviceProperties failed"; cudaGetLastError(); return; }
   jit::Source src;
-  std::string why = jit::build_source(md, consts, s->a.C, prop.multiProcessorCount, c0, src);
+  std::string why = stat_model ? jit::build_source(md, consts, s->a.C, prop.multiProcessorCount, c0, src)
+                               : jit::build_source_full(md, consts, s->a.C, prop.multiProcessorCount, c0, src);
   if (!why.empty()) { s->jit_note = "not specialised: " + why; return; }
   if (src.plan.smem_bytes > (unsigned)prop.sharedMemPerBlockOptin) { s->jit_note = "not specialised: shared-memory plan does not fit"; return; }
   const unsigned long long key = jit::fnv1a(src.generated, jit::fnv1a(src.prelude));
@@ -1394,7 +1396,7 @@ static void try_jit(amwg_sampler* s, const amwg_model* md) {
   s->jit_smem = src.plan.smem_bytes;
   s->jit_threads = src.plan.threads;
   char note[256];
-  snprintf(note, sizeof note, "specialised sweep: %d threads x %d CTAs/SM, %u B shared memory, %d resident column(s)%s%s%s", src.plan.threads, src.plan.minblocks,
+  snprintf(note, sizeof note, "specialised %s: %d threads x %d CTAs/SM, %u B shared memory, %d resident column(s)%s%s%s", src.full ? "full-program sweep" : "sweep", src.plan.threads, src.plan.minblocks,
            src.plan.smem_bytes, src.plan.n_res, src.plan.stream_col >= 0 ? ", one streamed column" : "", src.plan.ws_smem ? ", working set in shared memory" : "",
            disk ? " (cubin from the disk cache)" : "");
   s->jit_note = note;
@@ -1787,7 +1789,9 @@ extern "C" int amwg_jit_compile_check(const amwg_model* md, uint64_t n_chains, c
   std::vector<double> consts(md->consts, md->consts + md->n_consts);
   if (consts.empty()) consts.push_back(0.0);
   jit::Source src;
-  std::string why = jit::build_source(md, consts, n_chains ? n_chains : 1, 148, -0.9189385332046727, src);
+  const bool stat_model = md->comp_prog && md->n_terms > 0 && md->stat_prog >= 0;
+  std::string why = stat_model ? jit::build_source(md, consts, n_chains ? n_chains : 1, 148, -0.9189385332046727, src)
+                               : jit::build_source_full(md, consts, n_chains ? n_chains : 1, 148, -0.9189385332046727, src);
   if (!why.empty()) { put(log, log_cap, why); return 1; }
   put(src_out, src_cap, src.prelude + src.generated);
   std::vector<char> cubin;

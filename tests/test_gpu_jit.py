@@ -134,3 +134,57 @@ def test_expression_means_int_parameter_and_bounds(gpu_pkg, monkeypatch):
     for name in ("a", "k", "s", "prec"):
         assert _agreement(da[name][:, :, None], db[name][:, :, None]) > 0.99, name
     assert np.all(db["k"] == np.round(db["k"])) and np.all(np.abs(db["k"]) <= 20)
+
+
+# ---- the full-program form (amwg_jit_full_kernel.cuh): the same operations in the same order as the interpreter -> the same bits ----
+def _bit_equal(da, db):
+    for k in da:
+        x, y = np.asarray(da[k], np.float64), np.asarray(db[k], np.float64)
+        assert x.shape == y.shape and (x.view(np.uint64) == y.view(np.uint64)).all(), k
+
+
+@pytest.mark.parametrize("name", ["spike_where", "spike_literal", "complex_literal", "complex_where", "norm_faithful", "norm_faithful_derived",
+                                  "multi_bern"])
+def test_full_program_specialisation_is_bit_identical_to_the_interpreter(gpu_pkg, monkeypatch, name):
+    pkg = gpu_pkg
+    ld, mcmc = pkg.ld, pkg.mcmc
+    rng = np.random.default_rng(5)
+    y = (rng.random(100) < 0.7).astype(float).tolist()
+    nb = [int(v) for v in rng.integers(5, 30, 12)]
+    opts = {}
+    if name == "spike_where":
+        P, f, d = models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y}
+    elif name == "spike_literal":
+        P, f, d = models.PARAMS_SPIKE, models.spike_bern_literal(ld), {"x": y}
+    elif name == "complex_literal":
+        P, f, d = models.PARAMS_COMPLEX, models.complex_model_post_literal(ld), nb
+    elif name == "complex_where":
+        P, f, d = models.PARAMS_COMPLEX, models.complex_model_post(ld, mcmc), nb
+    elif name == "norm_faithful":
+        P, f, d, opts = models.PARAMS_NORM, models.norm_post_readme(ld), rng.normal(184.5, 4.5, 64).tolist(), {"faithful": True}
+    elif name == "norm_faithful_derived":
+        def f(state, data):
+            lp = 0
+            lp += ld.norm(state.mu, 0, 100)
+            lp += ld.unif(state.sigma, 0, 100)
+            for i in range(len(data)):
+                lp += ld.norm(data[i], state.mu, state.sigma)
+            state.cv = state.sigma / state.mu
+            return lp
+        P, d, opts = {"mu": {"type": "real", "init": 180}, "sigma": {"type": "real", "lower": 0, "init": 5}}, rng.normal(184.5, 4.5, 64).tolist(), {"faithful": True}
+    else:
+        P = {"x": {"type": "binary", "dim": [2, 2]}}
+        f, d = models.multi_bern_dens(mcmc), None
+    a, b = _pair(pkg, monkeypatch, P, f, d, 4096 + 37, **opts)          # a ragged last CTA
+    assert "full-program" in b.jit_status()[1]
+    for s in (a, b):
+        s.burn(120)                                   # crosses two adaptation batches
+    _bit_equal(a.sample(25), b.sample(25))
+    _bit_equal({"lp": a.log_post()}, {"lp": b.log_post()})
+    for s in (a, b):
+        s.burn(7)
+    _bit_equal(a.sample(6), b.sample(6))
+    ia, ib = a.info()["steppers"][0], b.info()["steppers"][0]
+    for k in ia:
+        if isinstance(ia[k], dict) and "prop_log_scale" in ia[k]:
+            assert np.array_equal(np.asarray(ia[k]["prop_log_scale"]), np.asarray(ib[k]["prop_log_scale"])), k

@@ -59,14 +59,38 @@ def test_expression_means_and_derived_quantities(pkg):
     assert "jit_derived" in src and "ld_gamma(" in src and "sum_sq_dev(" in src.split("jit_stat_extra")[1]
 
 
-def test_ineligible_models_keep_the_interpreter(pkg):
+def test_full_program_models_specialise_too(pkg):
+    """models that evaluate all of log_post at every step (binary parameters, `faithful` lowerings): the program itself, per
+    configuration of the binary components, printed as straight-line code (amwg_jit_full_kernel.cuh)"""
     y = (np.random.default_rng(2).random(64) < 0.5).astype(float)
     s = _model_only(pkg, models.PARAMS_SPIKE, models.spike_bern(pkg.ld, pkg.mcmc), {"x": y.tolist()})
-    rc, msg, _ = s.jit_compile_check()
-    assert rc == 1 and "no pre-evaluated statistics" in msg
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "0 bytes spill stores" in msg and "#define JFULL 1" in src
+    assert "jit_plate_bern(" in src and "jit_prog_0" in src and "jit_prog_1" not in src
+    # the reference's literal `if (m === 0)`: one program per configuration of m, chosen by the value the evaluation sees
+    s = _model_only(pkg, models.PARAMS_SPIKE, models.spike_bern_literal(pkg.ld), {"x": y.tolist()})
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "jit_prog_1" in src and "switch (0 | ((CM(1) != 0.0) ? 1 : 0))" in src
+    # int + binary + real parameters, negative-binomial likelihood in a loop (tests/test_data.js:154-171)
+    x = [int(v) for v in np.random.default_rng(3).integers(5, 30, 12)]
+    s = _model_only(pkg, models.PARAMS_COMPLEX, models.complex_model_post_literal(pkg.ld), x)
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "ld_nbinom(" in src and "js_round" not in src.split("jit_logpost")[0]      # rounding of int proposals is the skeleton's
+    # the bit-faithful lowering of the headline model: the N-point sum as a loop over the resident column, in data order
     from conftest import config2_data
     s = _model_only(pkg, models.PARAMS_NORM, models.norm_post_readme(pkg.ld), config2_data().tolist(), faithful=True)
-    assert s.jit_compile_check()[0] == 1
+    rc, msg, src = s.jit_compile_check()
+    assert rc == 0, msg
+    assert "for (int i_" in src or "LD(" in src
+
+
+def test_models_with_a_term_cache_keep_the_interpreter(pkg):
+    s = _model_only(pkg, models.PARAMS_HIER_BINOM, models.hierarchical_binomial_post(pkg.ld, pkg.mcmc), models.BINOM_DATA)
+    rc, msg, _ = s.jit_compile_check()
+    assert rc == 1 and "term cache" in msg
 
 
 def test_deeply_nested_expressions_are_refused_not_corrupted(pkg):
