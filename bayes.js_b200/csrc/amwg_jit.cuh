@@ -136,6 +136,7 @@ struct Plan {                                                  // shared-memory 
   int ring_off = 0, ring_stages = 4, ring_tile = 1024;         // tile in doubles
   int ws_smem = 0, ws_off = 0;
   unsigned smem_bytes = 0;
+  std::vector<int> bern_mask_off;                              // per plate: byte offset of a BERN_IID plate's bit mask in smem, -1 none (full-program form)
 };
 
 struct Source {
@@ -385,7 +386,9 @@ static bool emit_range(const GenCtx& gc, const std::vector<Inst>& inst, size_t i
           em.os << "    lp = lp + jit_norm_factorised(" << lit((double)pq.n) << ", sum_sq_dev(reinterpret_cast<const double*>(smem + " << boff << "), smem_u32(smem) + "
                 << boff << "u, " << pq.n << ", " << x << "), " << y << ");\n";
         } else if (pq.kind == AMWG_PLATE_BERN_IID) {
-          em.os << "    lp = jit_plate_bern(smem_u32(smem) + " << boff << "u, " << pq.n << ", " << x << ", lp);\n";
+          const int mo = in.a < (int)gc.plan->bern_mask_off.size() ? gc.plan->bern_mask_off[in.a] : -1;
+          if (mo >= 0) em.os << "    lp = jit_plate_bern_mask<" << pq.n << ">(smem, " << boff << "u, " << mo << "u, " << x << ", lp);\n";
+          else em.os << "    lp = jit_plate_bern(smem_u32(smem) + " << boff << "u, " << pq.n << ", " << x << ", lp);\n";
         } else if (pq.kind == AMWG_PLATE_NORM_GROUPED) {        // operand A = sd; points sorted by group, starts in col[1]
           const int c1 = pq.col[1];
           if (c1 < 0 || c1 >= md->n_columns || gc.plan->col_smem_off[c1] < 0) { why = "a plate's column is not resident"; return false; }
@@ -834,6 +837,17 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
     off += bytes;
   }
   pl.n_res = (int)pl.res_col.size();
+  // Bernoulli plates: the 0/1 column as a bit mask (+ one word: "some point is neither 0 nor 1"), built once per launch by the CTA
+  pl.bern_mask_off.assign(std::max(md->n_plates, 0), -1);
+  std::vector<long long> bm_plate;
+  for (int q = 0; q < md->n_plates; ++q) {
+    const amwg_plate& pq = md->plates[q];
+    if (pq.kind != AMWG_PLATE_BERN_IID || pq.n < 1 || pq.col[0] < 0 || pq.col[0] >= md->n_columns) continue;
+    if (pq.iparam[2] < 0 || (long long)pq.iparam[2] + pq.n > md->columns[pq.col[0]].n) return "a plate runs past its column";
+    off = (unsigned)pad16(off);
+    pl.bern_mask_off[q] = (int)off; bm_plate.push_back(q);
+    off += 4u * (unsigned)((pq.n + 31) / 32 + 1);
+  }
   { std::string e = choose_shape(pl, off, sizeof(double) * (size_t)D, n_chains, sm_count); if (!e.empty()) return e; }
 
   std::ostringstream tables, funcs;
@@ -918,6 +932,14 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
   std::vector<long long> a1, b1, c1;
   for (int k = 0; k < pl.n_res; ++k) { a1.push_back(pl.res_off[k]); b1.push_back(pl.res_col[k]); c1.push_back(pl.res_bytes[k]); }
   int_table("__constant__ unsigned", "JRES_OFF", a1); int_table("__constant__ int", "JRES_COL", b1); int_table("__constant__ unsigned", "JRES_BYTES", c1);
+  {
+    std::vector<long long> bd, bn, bo;
+    for (long long q : bm_plate) {
+      const amwg_plate& pq = md->plates[q];
+      bd.push_back(pl.col_smem_off[pq.col[0]] + 8 * pq.iparam[2]); bn.push_back(pq.n); bo.push_back(pl.bern_mask_off[q]);
+    }
+    int_table("__constant__ unsigned", "JBERN_DATA", bd); int_table("__constant__ int", "JBERN_N", bn); int_table("__constant__ unsigned", "JBERN_MASK", bo);
+  }
   t2 << "__device__ const long long KCB[" << std::max(md->n_consts, 1) << "] = {";
   for (int i = 0; i < md->n_consts; ++i) t2 << (i ? "," : "") << bits(consts[i]);
   if (md->n_consts == 0) t2 << "0LL";
@@ -927,7 +949,7 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
   std::ostringstream pre;
   pre << "#define JFULL 1\n#define JD " << D << "\n#define JP " << P << "\n#define JTHREADS " << pl.threads << "\n#define JMINB " << pl.minblocks
       << "\n#define JWS_SMEM " << pl.ws_smem << "\n#define JWS_OFF " << pl.ws_off << "\n#define JN_DERIVED " << md->n_derived << "\n#define JMAX_DIM0 " << max_dim0
-      << "\n#define JMAXCOL " << kMaxColumns << "\n#define JN_RES " << pl.n_res << "\n#define JRES_TOTAL_BYTES " << res_total << "u\n#define JNORM_C0 " << lit(norm_c0)
+      << "\n#define JMAXCOL " << kMaxColumns << "\n#define JN_BERN " << bm_plate.size() << "\n#define JN_RES " << pl.n_res << "\n#define JRES_TOTAL_BYTES " << res_total << "u\n#define JNORM_C0 " << lit(norm_c0)
       << "\n#define AMWG_REAL 0\n#define AMWG_INT 1\n#define AMWG_BINARY 2\n#define AMWG_NACC 4\n";
   src.prelude = pre.str();
   // the order inside the generated header: tables the programs use, parameter tables, programs

@@ -32,6 +32,29 @@ __device__ __forceinline__ double jit_plate_bern(unsigned saddr, int n, double p
   }
   return lp;
 }
+// The same sum with the column read as a bit mask (built once per launch, below): per point one bit test, a select and the add --
+// the adds stay sequential and in data order (each one rounds), which is all that bit-faithfulness asks for.
+template <int N>
+__device__ __forceinline__ double jit_plate_bern_mask(const unsigned char* smem, unsigned data_off, unsigned mask_off, double p, double lp) {
+  const unsigned* __restrict__ mask = reinterpret_cast<const unsigned*>(smem + mask_off);
+  if (mask[(N + 31) / 32] != 0u) return jit_plate_bern(smem_u32(smem) + data_off, N, p, lp);   // a point that is neither 0 nor 1
+  const double l1 = js_log(1.0 * p + (1 - 1.0) * (1 - p));
+  const double l0 = js_log(0.0 * p + (1 - 0.0) * (1 - p));
+#define JBERN_ADD(b) lp = lp + ((m >> (b)) & 1u ? l1 : l0)          // SASS: R2P per 7 points, 2 FSEL + 1 DADD per point
+#pragma unroll 1
+  for (int w = 0; w < N / 32; ++w) {
+    const unsigned m = mask[w];
+#pragma unroll
+    for (int b = 0; b < 32; ++b) JBERN_ADD(b);
+  }
+  if (N % 32) {
+    const unsigned m = mask[N / 32];
+#pragma unroll
+    for (int b = 0; b < N % 32; ++b) JBERN_ADD(b);
+  }
+#undef JBERN_ADD
+  return lp;
+}
 __device__ __forceinline__ double jit_norm_factorised(double n, double S, double sd) { return n * (JNORM_C0 - js_log(sd)) - S / (2 * sd * sd); }
 
 }  // namespace amwg
@@ -63,6 +86,22 @@ extern "C" __global__ void __launch_bounds__(JTHREADS, JMINB) amwg_jit_sweep(con
     for (int k = 0; k < JN_RES; ++k) tma_bulk_g2s(smem + JRES_OFF[k], A.col[JRES_COL[k]], JRES_BYTES[k], &bar_res);
   }
   mbar_wait(&bar_res, 0);
+#endif
+#if JN_BERN > 0
+  for (int k = 0; k < JN_BERN; ++k) {                           // 0/1 columns -> bit masks, one ballot per 32 points
+    const int n = JBERN_N[k];
+    unsigned* mask = reinterpret_cast<unsigned*>(smem + JBERN_MASK[k]);
+    if (threadIdx.x == 0) mask[(n + 31) / 32] = 0u;
+    __syncthreads();
+    for (int base = (int)(threadIdx.x & ~31u); base < n; base += JTHREADS) {
+      const int i = base + (int)(threadIdx.x & 31u);
+      const double yi = i < n ? lds_f64_sa(smem_u32(smem) + JBERN_DATA[k] + 8u * (unsigned)i) : 0.0;
+      const unsigned ones = __ballot_sync(0xffffffffu, yi == 1.0);
+      const unsigned bad = __ballot_sync(0xffffffffu, !(yi == 1.0 || yi == 0.0));
+      if ((threadIdx.x & 31u) == 0) { mask[base >> 5] = ones; if (bad) atomicOr(&mask[(n + 31) / 32], 1u); }
+    }
+  }
+  __syncthreads();
 #endif
   if (!valid) return;                                           // no CTA-wide step follows: threads past the last chain are done
 

@@ -144,7 +144,7 @@ def _bit_equal(da, db):
 
 
 @pytest.mark.parametrize("name", ["spike_where", "spike_literal", "complex_literal", "complex_where", "norm_faithful", "norm_faithful_derived",
-                                  "multi_bern"])
+                                  "multi_bern", "spike_ragged", "spike_bad_point"])
 def test_full_program_specialisation_is_bit_identical_to_the_interpreter(gpu_pkg, monkeypatch, name):
     pkg = gpu_pkg
     ld, mcmc = pkg.ld, pkg.mcmc
@@ -154,6 +154,10 @@ def test_full_program_specialisation_is_bit_identical_to_the_interpreter(gpu_pkg
     opts = {}
     if name == "spike_where":
         P, f, d = models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y}
+    elif name == "spike_ragged":                     # 77 points: two full mask words and a 13-bit tail
+        P, f, d = models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y[:77]}
+    elif name == "spike_bad_point":                  # a point that is neither 0 nor 1: ld.bern gives -Infinity, the sum stays sequential
+        P, f, d = models.PARAMS_SPIKE, models.spike_bern(ld, mcmc), {"x": y[:40] + [2.0] + y[41:]}
     elif name == "spike_literal":
         P, f, d = models.PARAMS_SPIKE, models.spike_bern_literal(ld), {"x": y}
     elif name == "complex_literal":
