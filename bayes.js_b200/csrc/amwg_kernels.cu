@@ -273,8 +273,11 @@ __device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const E
 //
 // exp(): table-driven, 2^(j/256) (256 entries in shared memory, filled once per CTA) times a degree-4 polynomial on
 // |r| <= ln2/512 (truncation 4e-17 relative): 9 fp64-pipe instructions including the accumulation, against ~25 for exp().
+__device__ __noinline__ double exp_acc_slow(double x, double s) { return s + exp(x); }
 __device__ __forceinline__ double exp_acc(double x, unsigned tab_sa, double s) {       // s + exp(x)
-  if (!(fabs(x) < 690.0)) return s + exp(x);                      // huge, infinite or NaN arguments: the library function
+  // huge, infinite or NaN arguments: the library function (out of line). |x| < 690 is tested on the high word: integer pipe, the
+  // fp64 pipe is the bound
+  if (((unsigned)__double2hiint(x) & 0x7fffffffu) >= 0x40859000u) return exp_acc_slow(x, s);
   const double tm = fma(x, 369.3299304675746, 6755399441055744.0);      // x * 256/ln2 + 1.5*2^52: the integer lands in the low word
   const int ki = __double2loint(tm);
   const double kf = tm - 6755399441055744.0;
@@ -341,6 +344,77 @@ __device__ __forceinline__ void pois_rows(unsigned xsa, int rows, const double (
   }
 }
 
+// ---- the same rows on the fp64 tensor core (K = 8, a full warp) ------------------------------------------------------------------
+// eta[row, chain] = sum_k X[row, k] beta[chain, k] is a GEMM: DMMA.8x8x4 (mma.sync m8n8k4 f64) forms it for 8 rows x 8 chains per
+// instruction, so a warp's 32 chains take 8 DMMAs per 8 rows instead of 64 DFMAs per thread -- and, what matters more, ONE
+// conflict-free LDS.128 per 8 rows instead of 32 broadcast LDS.128 (measured on this part, scripts/microbench/fp64_pipes.cu: a
+// broadcast LDS.128 costs 2.5 cycles of the SM's shared-memory pipe and overlaps poorly with the fp64 pipe; the per-thread form
+// spends as long on its loads as on its arithmetic. DMMA runs on the same fp64 pipe as DFMA at the same flop rate, 16 cycles each).
+// Fragment layout (PTX ISA, m8n8k4 .f64): lane = 4 * g + j. A: row g, one k per step; B: column (chain) g of the tile, one k per
+// step; C: row g, chains 2j and 2j + 1 of the tile. Lane j takes k = 2j (step 0) and k = 2j + 1 (step 1), adjacent in the row.
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+struct PoisMma {
+  double bf[4][2];        // B fragments: tile t (chains 8t..8t+7 of the warp), k step s
+  double acc[8];          // sum of exp(eta) over the rows this lane saw: tile t, chain 2j + e -> acc[2t + e]
+  __device__ __forceinline__ void init(const double (&beta)[8]) {
+    const unsigned lane = threadIdx.x & 31u, j = lane & 3u;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      bf[t][0] = bf[t][1] = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const double w = __shfl_sync(0xffffffffu, beta[k], 8 * t + (int)(lane >> 2));
+        if (k == (int)(2u * j)) bf[t][0] = w;
+        if (k == (int)(2u * j + 1u)) bf[t][1] = w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.0;
+  }
+  // `rows` rows (row-major, 8 doubles per row) starting at shared address xsa, in groups of 8; in a last, partial group the lanes
+  // of the missing rows compute on whatever follows in the tile and drop the result (a row of D depends on its own row of A only)
+  __device__ __forceinline__ void rows8(unsigned xsa, int rows, unsigned tab_sa) {
+    const unsigned lane = threadIdx.x & 31u;
+    unsigned addr = xsa + (lane >> 2) * 64u + (lane & 3u) * 16u;
+    int left = rows - (int)(lane >> 2);                         // this lane's row of the group exists while left > 0
+    const int groups = (rows + 7) >> 3;
+#pragma unroll 1
+    for (int g = 0; g < groups; ++g, left -= 8, addr += 512u) {
+      const double2 a = lds_f64x2(addr);
+      const bool mine = left > 0;
+#pragma unroll
+      for (int t = 0; t < 4; t += 2) {
+        double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+        dmma884(c00, c01, a.x, bf[t][0]); dmma884(c10, c11, a.x, bf[t + 1][0]);
+        dmma884(c00, c01, a.y, bf[t][1]); dmma884(c10, c11, a.y, bf[t + 1][1]);
+        if (mine) {
+          acc[2 * t] = exp_acc(c00, tab_sa, acc[2 * t]); acc[2 * t + 1] = exp_acc(c01, tab_sa, acc[2 * t + 1]);
+          acc[2 * t + 2] = exp_acc(c10, tab_sa, acc[2 * t + 2]); acc[2 * t + 3] = exp_acc(c11, tab_sa, acc[2 * t + 3]);
+        }
+      }
+    }
+  }
+  // this lane's chain: the eight row classes added up, then the total moved to the lane that owns the chain
+  __device__ __forceinline__ double total() {
+    const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+      acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    double S = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const double w = __shfl_sync(0xffffffffu, acc[i], (int)((lane & 7u) >> 1));
+      if (i == (int)(2u * (lane >> 3) + (lane & 1u))) S = w;
+    }
+    return S;
+  }
+};
+
 // rows from global / L2 when neither residency nor the ring applies (models whose chains take different steps per sweep)
 template <int K>
 __device__ __forceinline__ void pois_rows_global(const double* __restrict__ X, int rows, const double (&beta)[K], unsigned tab_sa, double& s0, double& s1) {
@@ -378,10 +452,19 @@ __device__ __forceinline__ double pois_plate_k(Ctx& ctx, const amwg_plate& pl, c
         const int rows = min(R, n - t * R);
         ring_issue(ctx, t, X + (size_t)t * R * K, (unsigned)((rows * K * 8 + 15) & ~15));
       }
+    // K = 8: the dot products on the tensor core (every thread of the CTA is here: whole warps)
+    [[maybe_unused]] PoisMma mm;
+    if constexpr (K == 8) mm.init(beta);
     for (int t = 0; t < ntiles; ++t) {
       const int st = t & 1;
       mbar_wait(&ctx.ring_bar[st], ((st ? u1 : u0) + (unsigned)(t >> 1)) & 1u);
-      pois_rows<K>(ctx.ring_saddr + (unsigned)st * kRingStageBytes, min(R, n - t * R), beta, tab_sa, s0, s1);
+      const unsigned tile_sa = ctx.ring_saddr + (unsigned)st * kRingStageBytes;
+      const int rows = min(R, n - t * R);
+      if constexpr (K == 8) {
+        mm.rows8(tile_sa, rows, tab_sa);
+      } else {
+        pois_rows<K>(tile_sa, rows, beta, tab_sa, s0, s1);
+      }
       __syncthreads();
       if (threadIdx.x == 0 && t + 2 < ntiles) {
         const int rows = min(R, n - (t + 2) * R);
@@ -389,6 +472,7 @@ __device__ __forceinline__ double pois_plate_k(Ctx& ctx, const amwg_plate& pl, c
       }
     }
     if (threadIdx.x == 0) { ctx.ring_uses[0] = u0 + (unsigned)((ntiles + 1) >> 1); ctx.ring_uses[1] = u1 + (unsigned)(ntiles >> 1); }
+    if constexpr (K == 8) s0 = s0 + mm.total();
   }
   return (lin - (s0 + s1)) - stats[K];
 }

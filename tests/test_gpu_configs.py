@@ -266,3 +266,35 @@ def test_pooled_oracle_ks_on_the_production_path(gpu_pkg, orc):
         allv = np.concatenate([a, b])
         d = np.max(np.abs(np.searchsorted(a, allv, side="right") / a.size - np.searchsorted(b, allv, side="right") / b.size))
         assert b.size >= 100000 and d < 0.01, (name, d)
+
+
+def test_poisson_plate_on_the_tensor_core_matches_numpy(gpu_pkg):
+    """K = 8 with X streamed through the tile ring: the dot products run as DMMA.8x8x4 (csrc PoisMma). The carried log_post of every
+    chain (the plate's value at the last accepted proposal) against a float64 numpy evaluation at the chain's state; n = 20003 rows:
+    partial last tile, partial last group of 8 rows; 200 chains: a partial CTA and a partial warp."""
+    K, n = 8, 20003
+    rng = np.random.default_rng(21)
+    X = np.column_stack([np.ones(n), rng.normal(0, 0.4, (n, K - 1))])
+    beta_true = np.concatenate([[0.3], rng.normal(0, 0.25, K - 1)])
+    yy = rng.poisson(np.exp(X @ beta_true)).astype(float)
+    params = {"beta": {"type": "real", "dim": [K]}}
+    mcmc, ld = gpu_pkg.mcmc, gpu_pkg.ld
+    s = mcmc.AmwgSampler(params, poisreg_post(ld, mcmc, K), {"y": yy.tolist(), "X": X.tolist()}, {"chains": 200, "seed": 3})
+    assert s.program_summary()[-1] == f"plate POIS_LOGLIN n={n} K={K}"
+    from scipy.special import gammaln
+    lfact = gammaln(yy + 1.0).sum()
+
+    def numpy_lp(beta):                                            # [chains, K]
+        eta = beta @ X.T
+        prior = (-0.5 * np.log(2 * np.pi) - np.log(10.0) - beta * beta / 200.0).sum(axis=1)
+        return prior + (eta * yy).sum(axis=1) - np.exp(eta).sum(axis=1) - lfact
+    for burn in (0, 25, 60):
+        if burn:
+            s.burn(burn)
+        beta = np.asarray(s.state["beta"], np.float64).reshape(200, K)
+        got, want = np.asarray(s.log_post(), np.float64), numpy_lp(beta)
+        assert np.allclose(got, want, rtol=2e-12, atol=0), (burn, np.max(np.abs(got - want) / np.abs(want)))
+    assert np.unique(beta[:, 1]).size > 150                        # the chains have moved, each on its own
+    s.burn(600)
+    b = np.asarray(s.state["beta"], np.float64).reshape(200, K)
+    assert np.all(np.abs(b.mean(axis=0) - beta_true) < 0.05)
