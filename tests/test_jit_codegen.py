@@ -135,3 +135,30 @@ def test_parameter_array_indexed_out_of_bounds_is_refused(pkg):
     with pytest.raises(pkg.JsThrow, match="outside its bounds"):
         _model_only(pkg, P, hier, {"y": y, "g": g})
     _model_only(pkg, P, hier, {"y": y, "g": g - 1})                 # 0-based ids are fine
+
+
+def test_every_golden_model_is_specialised_or_says_why(pkg):
+    """Code generation over the reference's own fixtures (the 32 sampler scenarios of tests/golden/reference_js.json, `faithful`
+    lowering as the golden tests run them): each model either compiles for sm_100a or is turned down for a stated reason -- the
+    generator never fails on a valid program. (With AMWG_JIT=1 the GPU golden tests run these kernels against the vectors.)"""
+    import copy
+    import golden_util as gu
+    seen, compiled, declined = set(), 0, {}
+    for case in gu.load()["samplers"]:
+        key = (case["log_post"], str(case["params"]), str(case["options"]))
+        if key in seen:
+            continue
+        seen.add(key)
+        _c, py_model, params, data, _dc = gu.resolve_case(case, pkg)
+        opts = copy.deepcopy(case["options"]) or {}
+        opts.update({"chains": 4096, "faithful": True, "_model_only": True})
+        s = pkg.mcmc.AmwgSampler(copy.deepcopy(params), py_model, data, opts)
+        rc, msg, src = s.jit_compile_check()
+        assert rc in (0, 1), (case["name"], msg)
+        if rc == 0:
+            compiled += 1
+            assert "jit_logpost" in src and "ok: cubin" in msg, case["name"]
+        else:
+            declined[msg.splitlines()[0]] = declined.get(msg.splitlines()[0], 0) + 1
+    assert compiled >= 5, (compiled, declined)
+    assert set(declined) <= {"the model steps with a term cache"}, declined
