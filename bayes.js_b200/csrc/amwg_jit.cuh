@@ -174,7 +174,6 @@ struct Inst {
   std::vector<Insn> ins;
   int moved = -1;                                              // the component this instance steps (-1: none, e.g. stat / derived code)
 };
-struct Plan;
 struct GenCtx {
   const amwg_model* md = nullptr;
   const Plan* plan = nullptr;                                  // shared-memory offsets of the resident columns (full-program code)
@@ -878,8 +877,6 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
     }
     return "";
   };
-  funcs << "namespace amwg {\n#define LD(o) lds_f64_sa(smem_u32(smem) + (o))\n";
-  std::ostringstream body;
   for (int v = 0; v < n_var; ++v) {
     const int pc = md->n_variant_comps ? md->variant_logpost[v] : md->logpost_prog;
     std::string e = emit_program(pc, "jit_prog_" + std::to_string(v), false);
@@ -901,7 +898,6 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
     }
     return e;
   };
-  funcs << tables.str();
   funcs << "__device__ __forceinline__ double jit_logpost(unsigned char* smem, const double* __restrict__ sp, const unsigned long long ss, const int moved, const double val) {\n";
   if (n_var == 1) funcs << "  return jit_prog_0(smem, sp, ss, moved, val);\n";
   else {
@@ -952,10 +948,8 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
       << "\n#define JMAXCOL " << kMaxColumns << "\n#define JN_BERN " << bm_plate.size() << "\n#define JN_RES " << pl.n_res << "\n#define JRES_TOTAL_BYTES " << res_total << "u\n#define JNORM_C0 " << lit(norm_c0)
       << "\n#define AMWG_REAL 0\n#define AMWG_INT 1\n#define AMWG_BINARY 2\n#define AMWG_NACC 4\n";
   src.prelude = pre.str();
-  // the order inside the generated header: tables the programs use, parameter tables, programs
-  std::string f = funcs.str();
-  const std::string ns = "namespace amwg {\n#define LD(o) lds_f64_sa(smem_u32(smem) + (o))\n";
-  src.generated = ns + t2.str() + f.substr(ns.size()) + "}  // namespace amwg\n";
+  // the generated header: parameter / staging tables and constants, tables the programs index, then the programs and their dispatch
+  src.generated = "namespace amwg {\n#define LD(o) lds_f64_sa(smem_u32(smem) + (o))\n" + t2.str() + tables.str() + funcs.str() + "}  // namespace amwg\n";
   src.full = true;
   return "";
 }

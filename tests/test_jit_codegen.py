@@ -67,7 +67,7 @@ def test_full_program_models_specialise_too(pkg):
     rc, msg, src = s.jit_compile_check()
     assert rc == 0, msg
     assert "0 bytes spill stores" in msg and "#define JFULL 1" in src
-    assert "jit_plate_bern(" in src and "jit_prog_0" in src and "jit_prog_1" not in src
+    assert "jit_plate_bern_mask<64>(" in src and "#define JN_BERN 1" in src and "jit_prog_0" in src and "jit_prog_1" not in src
     # the reference's literal `if (m === 0)`: one program per configuration of m, chosen by the value the evaluation sees
     s = _model_only(pkg, models.PARAMS_SPIKE, models.spike_bern_literal(pkg.ld), {"x": y.tolist()})
     rc, msg, src = s.jit_compile_check()
