@@ -274,22 +274,29 @@ __device__ __noinline__ double plate_norm_grouped(const Ctx& ctx, int q, const E
 // exp(): table-driven, 2^(j/256) (256 entries in shared memory, filled once per CTA) times a degree-4 polynomial on
 // |r| <= ln2/512 (truncation 4e-17 relative): 9 fp64-pipe instructions including the accumulation, against ~25 for exp().
 __device__ __noinline__ double exp_acc_slow(double x, double s) { return s + exp(x); }
-__device__ __forceinline__ double exp_acc(double x, unsigned tab_sa, double s) {       // s + exp(x)
-  // huge, infinite or NaN arguments: the library function (out of line). |x| < 690 is tested on the high word: integer pipe, the
-  // fp64 pipe is the bound
-  if (((unsigned)__double2hiint(x) & 0x7fffffffu) >= 0x40859000u) return exp_acc_slow(x, s);
-  const double tm = fma(x, 369.3299304675746, 6755399441055744.0);      // x * 256/ln2 + 1.5*2^52: the integer lands in the low word
+// the constants whose low words are not zero come from the constant bank (an operand of DFMA, no instruction): as literals each
+// costs two moves per use at the sweep kernels' register cap
+__constant__ double kExpC[5] = {369.3299304675746 /* 256/ln2 */, -0.0027076061742263846 /* -HI */, 1.6409824502660487e-13 /* LO: ln2/256 = HI - LO */,
+                                1.0 / 24.0, 1.0 / 6.0};
+// |x| < 690, tested on the high word (integer pipe: the fp64 pipe is the bound); huge, infinite and NaN arguments fail
+__device__ __forceinline__ bool exp_in_range(double x) { return ((unsigned)__double2hiint(x) & 0x7fffffffu) < 0x40859000u; }
+__device__ __forceinline__ double exp_acc_fast(double x, unsigned tab_sa, double s) {   // s + exp(x) for x in range
+  const double tm = fma(x, kExpC[0], 6755399441055744.0);          // x * 256/ln2 + 1.5*2^52: the integer lands in the low word
   const int ki = __double2loint(tm);
   const double kf = tm - 6755399441055744.0;
-  double r = fma(kf, -0.0027076061742263846, x);                   // Cody-Waite: ln2/256 = HI (32 bits) + LO
-  r = fma(kf, 1.6409824502660487e-13, r);
-  double p = fma(r, 1.0 / 24.0, 1.0 / 6.0);
+  double r = fma(kf, kExpC[1], x);                                 // Cody-Waite: ln2/256 = HI (32 bits) + LO
+  r = fma(kf, kExpC[2], r);
+  double p = fma(r, kExpC[3], kExpC[4]);
   p = fma(p, r, 0.5);
   p = fma(p, r, 1.0);
   p = fma(p, r, 1.0);
   const double T = lds_f64_sa(tab_sa + 8u * (unsigned)(ki & 255));
   const double Ts = __hiloint2double(__double2hiint(T) + ((ki >> 8) << 20), __double2loint(T));      // * 2^(ki >> 8)
   return fma(Ts, p, s);
+}
+__device__ __forceinline__ double exp_acc(double x, unsigned tab_sa, double s) {        // s + exp(x)
+  if (!exp_in_range(x)) return exp_acc_slow(x, s);                 // the library function, out of line
+  return exp_acc_fast(x, tab_sa, s);
 }
 
 template <int K>
@@ -390,8 +397,14 @@ struct PoisMma {
         dmma884(c00, c01, a.x, bf[t][0]); dmma884(c10, c11, a.x, bf[t + 1][0]);
         dmma884(c00, c01, a.y, bf[t][1]); dmma884(c10, c11, a.y, bf[t + 1][1]);
         if (mine) {
-          acc[2 * t] = exp_acc(c00, tab_sa, acc[2 * t]); acc[2 * t + 1] = exp_acc(c01, tab_sa, acc[2 * t + 1]);
-          acc[2 * t + 2] = exp_acc(c10, tab_sa, acc[2 * t + 2]); acc[2 * t + 3] = exp_acc(c11, tab_sa, acc[2 * t + 3]);
+          // one range test for the four values: no branches between their dependency chains, which then interleave
+          if (exp_in_range(c00) && exp_in_range(c01) && exp_in_range(c10) && exp_in_range(c11)) {
+            acc[2 * t] = exp_acc_fast(c00, tab_sa, acc[2 * t]); acc[2 * t + 1] = exp_acc_fast(c01, tab_sa, acc[2 * t + 1]);
+            acc[2 * t + 2] = exp_acc_fast(c10, tab_sa, acc[2 * t + 2]); acc[2 * t + 3] = exp_acc_fast(c11, tab_sa, acc[2 * t + 3]);
+          } else {
+            acc[2 * t] = exp_acc(c00, tab_sa, acc[2 * t]); acc[2 * t + 1] = exp_acc(c01, tab_sa, acc[2 * t + 1]);
+            acc[2 * t + 2] = exp_acc(c10, tab_sa, acc[2 * t + 2]); acc[2 * t + 3] = exp_acc(c11, tab_sa, acc[2 * t + 3]);
+          }
         }
       }
     }
