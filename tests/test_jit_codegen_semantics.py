@@ -18,6 +18,7 @@ import pytest
 
 import models
 import prog_eval
+from conftest import NORM_DATA
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "bayes.js_b200", "csrc")
@@ -176,12 +177,162 @@ def _cases(pkg):
                                   rng.normal(184.5, 4.5, 64).tolist(), {"faithful": True}),
         "multi_bern": ({"x": {"type": "binary", "dim": [2, 2]}}, models.multi_bern_dens(mcmc), None, {}),
         "beta_bern_faithful": (models.PARAMS_THETA, models.beta_bern(ld), {"x": y}, {"faithful": True}),
+        # tests/test_data.js:80-91: the Normal model that also writes the derived quantity par.var = sigma^2
+        "norm_test_faithful": (models.PARAMS1, models.norm_post_test(ld), NORM_DATA, {"faithful": True}),
     }
 
 
 @pytest.mark.parametrize("name", ["spike_where", "spike_literal", "spike_bad_point", "complex_literal", "complex_where", "norm_faithful_derived",
-                                  "multi_bern", "beta_bern_faithful"])
+                                  "multi_bern", "beta_bern_faithful", "norm_test_faithful"])
 def test_generated_log_post_equals_the_program(pkg, orc, tmp_path, name):
     params, f, data, opts = _cases(pkg)[name]
     hp = HostProgram(pkg, orc, tmp_path, params, f, data, **opts)
     hp.check(np.random.default_rng(11))
+
+
+# ---- the whole specialised kernel on the host: skeleton + generated code, one emulated thread per CTA -----------------------------
+KERNEL_SHIM = r'''
+#define __global__
+#define __launch_bounds__(...)
+#define __grid_constant__
+#define __shared__
+#define __align__(n)
+struct hs_dim3 { unsigned x = 0, y = 0, z = 0; };
+static hs_dim3 threadIdx, blockIdx, blockDim;
+static inline void __syncthreads() {}
+namespace amwg {
+alignas(16) unsigned char smem[1 << 18];                         // the CTA's dynamic shared memory (`extern __shared__ ... smem[]` in the kernel)
+static inline void mbar_init(unsigned long long*, unsigned) {}
+static inline void mbar_expect_tx(unsigned long long*, unsigned) {}
+static inline void mbar_wait(unsigned long long*, unsigned) {}
+static inline void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long*) { std::memcpy(dst, src, bytes); }
+}
+'''
+
+KERNEL_EXPORTS = r'''
+extern "C" {
+unsigned char* hs_kernel_smem() { return amwg::smem; }
+double hs_exp_of(double x) { return amwg::js_exp(x); }
+void hs_sweep(double* state, double* psd, int* acc, double* curr_lp, unsigned long long* perm, unsigned long long* rng_n,
+              unsigned long long C, unsigned long long first_chain, unsigned long long seed, long long n_sweeps, long long sample_i0,
+              long long thin, int record, int n_monitor, const int* monitor, double* out, const double** cols, int n_cols,
+              const unsigned char* adapting) {
+  amwg::JitArgs A{};
+  A.a.state = state; A.a.psd = psd; A.a.acc = acc; A.a.curr_lp = curr_lp; A.a.perm = perm; A.a.rng_n = rng_n;
+  A.a.C = C; A.a.first_chain = first_chain; A.a.seed = seed;
+  A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = sample_i0; A.sa.thin = thin; A.sa.record = record; A.sa.n_monitor = n_monitor;
+  A.sa.monitor = monitor; A.sa.out = out;
+  for (int k = 0; k < n_cols; ++k) A.col[k] = cols[k];
+  A.adapting = adapting;
+  g_smem_base = amwg::smem;
+  blockDim.x = 1; threadIdx.x = 0;
+  for (unsigned long long c = 0; c < C; ++c) { blockIdx.x = (unsigned)c; amwg::amwg_jit_sweep(A); }   // one thread per CTA: chain = blockIdx.x
+}
+}
+'''
+
+
+def _tma_structs():
+    text = open(os.path.join(CSRC, "amwg_tma.cuh")).read()
+    a = text.index("struct ChainArrays {")
+    b = text.index("// ---- TMA 1-D bulk copy + mbarrier")
+    return "namespace amwg {\n" + text[a:b] + "}  // namespace amwg\n"
+
+
+def _kernel_text(generated):
+    """csrc/amwg_jit_full_kernel.cuh as the host compiles it: the generated header spliced in where it is included, the one PTX fence
+    dropped (no mbarrier on the host), and the Bernoulli bit masks taken as given (the test builds them; the kernel's builder is a
+    warp-wide ballot, and the host runs one thread per CTA)."""
+    text = open(os.path.join(CSRC, "amwg_jit_full_kernel.cuh")).read()
+    lines = []
+    n_asm = 0
+    for ln in text.splitlines():
+        if "asm volatile(" in ln:
+            assert "fence.mbarrier_init" in ln, ln
+            n_asm += 1
+            continue
+        lines.append(ln)
+    assert n_asm == 1
+    text = "\n".join(lines)
+    inc = '#include "amwg_jit_generated.inc"'
+    assert text.count(inc) == 1
+    return text.replace(inc, generated + "\n#undef JN_BERN\n#define JN_BERN 0\n").replace("#pragma once", "")
+
+
+class HostKernel(HostProgram):
+    def __init__(self, pkg, orc, tmp_path, params, log_post, data, **opts):
+        self._tmp = tmp_path
+        super().__init__(pkg, orc, tmp_path, params, log_post, data, **opts)
+        s = self.s
+        m = s._model_keepalive[-1]
+        rc, msg, src = s.jit_compile_check()
+        assert rc == 0, msg
+        cut = src.index("namespace amwg {")
+        cpp = tmp_path / "kernel.cpp"
+        cpp.write_text(src[:cut] + HOST_PRELUDE + KERNEL_SHIM + _tma_structs() + _kernel_text(src[cut:]) + KERNEL_EXPORTS)
+        so = tmp_path / "kernel.so"
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "tests", "host_shim"),
+                            "-I" + CSRC, str(cpp), "-o", str(so)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-4000:]
+        self.K = K = C.CDLL(str(so))
+        K.hs_kernel_smem.restype = C.POINTER(C.c_ubyte)
+        K.hs_exp_of.restype, K.hs_exp_of.argtypes = C.c_double, [C.c_double]
+        # the masks the kernel's ballot loop would build: copied from the evaluation harness's staging buffer
+        ks = np.ctypeslib.as_array(K.hs_kernel_smem(), shape=(1 << 18,))
+        for k in range(self.lib.hs_n_bern()):
+            n, m0 = self.lib.hs_bern_n(k), self.lib.hs_bern_mask(k)
+            nb = 4 * ((n + 31) // 32 + 1)
+            ks[m0:m0 + nb] = self.smem[m0:m0 + nb]
+        self.init = np.array([m.init[c] for c in range(self.D)], dtype=np.float64)
+        self.n_params = int(m.n_params)
+
+    def run(self, chains, first_chain, seed, sweeps):
+        """`sweeps` sweeps of sample(): -> out[row][entry][chain] (row r = the state before sweep r), the final state and stream positions"""
+        D, Cn = self.D, chains
+        state = np.repeat(self.init[:, None], Cn, axis=1).copy()
+        psd = np.full((D, Cn), self.K.hs_exp_of(0.0))
+        acc = np.zeros((D, Cn), dtype=np.int32)
+        lp0 = self.lib.hs_logpost(self.init.ctypes.data_as(C.POINTER(C.c_double)), -1, 0.0)
+        curr = np.full(Cn, lp0)
+        perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
+        rng_n = np.zeros(Cn, dtype=np.uint64)
+        n_der = len(self.s._derived_names)
+        mon = np.arange(D + n_der, dtype=np.int32)
+        out = np.full((sweeps, mon.size, Cn), np.nan)
+        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
+        colp = (C.POINTER(C.c_double) * max(len(cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
+        adapting = np.ones(D, dtype=np.uint8)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        self.K.hs_sweep(p(state, C.c_double), p(psd, C.c_double), p(acc, C.c_int), p(curr, C.c_double), p(perm, C.c_uint64), p(rng_n, C.c_uint64),
+                        C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), C.c_longlong(0), C.c_longlong(1), 1,
+                        int(mon.size), p(mon, C.c_int), p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte))
+        return out, state, rng_n, acc
+
+
+@pytest.mark.parametrize("name,c_model,data_c", [
+    ("spike_where", "spike_bern", lambda d: {"x": np.asarray(d["x"], float)}),
+    ("spike_literal", "spike_bern", lambda d: {"x": np.asarray(d["x"], float)}),
+    ("complex_literal", "complex", lambda d: {"x": np.asarray(d, float)}),
+    ("multi_bern", "multi_bern_dens", lambda d: None),
+    ("beta_bern_faithful", "beta_bern", lambda d: {"x": np.asarray(d["x"], float)}),
+    ("norm_test_faithful", "norm_test", lambda d: np.asarray(d, float)),
+])
+def test_the_specialised_kernel_run_on_the_host_draws_what_the_oracle_draws(pkg, orc, tmp_path, name, c_model, data_c):
+    """The skeleton (csrc/amwg_jit_full_kernel.cuh) and the generated code, compiled for the host and run one emulated thread per CTA
+    -- shuffles, proposals, bounds, Metropolis and binary steps, sample recording -- against the CPU restatement of mcmc.js on the same
+    Philox streams: 45 recorded sweeps (inside the first adaptation batch: the batch update is a separate kernel) of 6 chains at a
+    global chain offset, bit for bit, and the same number of Math.random() calls consumed."""
+    params, f, data, opts = _cases(pkg)[name]
+    hk = HostKernel(pkg, orc, tmp_path, params, f, data, **opts)
+    chains, first, seed, sweeps = 6, 1000003, 17, 45
+    out, state, rng_n, acc = hk.run(chains, first, seed, sweeps)
+    ref = orc.run_model(c_model, data_c(data), params, chains=chains, first_chain=first, seed=seed, burn=0, sample=sweeps)
+    e = 0
+    for pname in hk.s.params:
+        n = int(np.prod(hk.s.params[pname]["dim"]))
+        got = np.moveaxis(out[:, e:e + n, :], 1, 2).reshape(np.asarray(ref[pname]).shape)     # [rows, chains, *dim]
+        assert np.array_equal(got.view(np.uint64), np.asarray(ref[pname], np.float64).view(np.uint64)), pname
+        e += n
+    for k, dname in enumerate(hk.s._derived_names):               # derived quantities are recorded with the state they belong to
+        assert np.array_equal(out[:, e + k, :].view(np.uint64), np.asarray(ref[dname], np.float64).reshape(sweeps, chains).view(np.uint64)), dname
+    assert np.all(rng_n >= sweeps) and np.unique(out[-1], axis=1).shape[1] > 1          # every chain drew, and not the same thing
