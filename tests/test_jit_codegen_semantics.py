@@ -336,3 +336,157 @@ def test_the_specialised_kernel_run_on_the_host_draws_what_the_oracle_draws(pkg,
     for k, dname in enumerate(hk.s._derived_names):               # derived quantities are recorded with the state they belong to
         assert np.array_equal(out[:, e + k, :].view(np.uint64), np.asarray(ref[dname], np.float64).reshape(sweeps, chains).view(np.uint64)), dname
     assert np.all(rng_n >= sweeps) and np.unique(out[-1], axis=1).shape[1] > 1          # every chain drew, and not the same thing
+
+
+# ---- the production lowering: the specialised statistics sweep (csrc/amwg_jit_kernel.cuh) on the host -------------------------------
+STAT_SHIM = KERNEL_SHIM + r'''
+static inline int atomicAdd(int* p, int v) { const int o = *p; *p = o + v; return o; }
+static inline int min(int a, int b) { return a < b ? a : b; }
+static inline int max(int a, int b) { return a > b ? a : b; }
+namespace amwg {
+static inline double2 lds_f64x2(unsigned a) { double2 v; std::memcpy(&v, g_smem_base + a, 16); return v; }
+}
+'''
+
+STAT_EXPORTS = r'''
+extern "C" {
+unsigned char* hs_kernel_smem() { return amwg::smem; }
+double hs_exp_of(double x) { return amwg::js_exp(x); }
+int hs_nt() { return JNT; }
+void hs_sweep(double* state, double* psd, int* acc, double* work /* [2 JNT + 2 JD][C] */, unsigned short* vseq, unsigned long long* perm,
+              unsigned long long* rng_n, unsigned long long C, unsigned long long first_chain, unsigned long long seed, long long n_sweeps,
+              int n_monitor, const int* monitor, double* out, const double** cols, int n_cols, const unsigned char* adapting) {
+  amwg::JitArgs A{};
+  A.a.state = state; A.a.psd = psd; A.a.acc = acc; A.a.perm = perm; A.a.rng_n = rng_n; A.a.vseq = vseq;
+  A.a.tval = work; A.a.tcand = work + (unsigned long long)JNT * C; A.a.bprop = work + 2ull * JNT * C; A.a.bcoin = work + (2ull * JNT + JD) * C;
+  A.a.C = C; A.a.first_chain = first_chain; A.a.seed = seed;
+  A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = 0; A.sa.thin = 1; A.sa.record = 1; A.sa.n_monitor = n_monitor; A.sa.monitor = monitor; A.sa.out = out;
+  for (int k = 0; k < n_cols; ++k) A.col[k] = cols[k];
+  A.adapting = adapting;
+  g_smem_base = amwg::smem;
+  blockDim.x = 1; threadIdx.x = 0;
+  for (unsigned long long c = 0; c < C; ++c) { blockIdx.x = (unsigned)c; amwg::amwg_jit_sweep(A); }
+}
+}
+'''
+
+
+def _sum_sq_text():
+    text = open(os.path.join(CSRC, "amwg_tma.cuh")).read()
+    a = text.index("// ---- plates: the O(N) likelihood sums")
+    b = text.index("#undef AMWG_ACC8", a)
+    return "namespace amwg {\n" + text[a:b] + "#undef AMWG_ACC8\n}  // namespace amwg\n"
+
+
+def _stat_kernel_text(generated):
+    text = open(os.path.join(CSRC, "amwg_jit_kernel.cuh")).read()
+    lines, n_asm = [], 0
+    for ln in text.splitlines():
+        if "asm volatile(" in ln:
+            assert "fence.mbarrier_init" in ln, ln
+            n_asm += 1
+            continue
+        lines.append(ln)
+    assert n_asm == 1
+    text = "\n".join(lines)
+    inc = '#include "amwg_jit_generated.inc"'
+    assert text.count(inc) == 1
+    return text.replace(inc, generated).replace("#pragma once", "")
+
+
+class HostStatKernel:
+    def __init__(self, pkg, orc, tmp_path, params, log_post, data, chains_hint=4096):
+        self.s = s = pkg.mcmc.AmwgSampler(params, log_post, data, {"chains": chains_hint, "_model_only": True})
+        self.prog, self.O = s._program, orc.lib()
+        assert self.prog.stat_prog >= 0
+        self.consts = prog_eval.fold_constants(self.prog, self.O)
+        m = s._model_keepalive[-1]
+        for i, v in enumerate(self.consts):
+            m.consts[i] = float(v)
+        rc, msg, src = s.jit_compile_check()
+        assert rc == 0, msg
+        self.src = src
+        cut = src.index("namespace amwg {")
+        cpp = tmp_path / "stat_kernel.cpp"
+        cpp.write_text(src[:cut] + HOST_PRELUDE + STAT_SHIM + _tma_structs() + _sum_sq_text() + _stat_kernel_text(src[cut:]) + STAT_EXPORTS)
+        so = tmp_path / "stat_kernel.so"
+        r = subprocess.run(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-w", "-I" + os.path.join(ROOT, "tests", "host_shim"),
+                            "-I" + CSRC, str(cpp), "-o", str(so)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-4000:]
+        self.K = K = C.CDLL(str(so))
+        K.hs_exp_of.restype, K.hs_exp_of.argtypes = C.c_double, [C.c_double]
+        self.D, self.NT, self.n_params = int(m.n_comp), K.hs_nt(), int(m.n_params)
+        assert self.NT == self.prog.n_terms
+        self.init = np.array([m.init[c] for c in range(self.D)], dtype=np.float64)
+
+    def run(self, chains, first_chain, seed, sweeps):
+        D, NT, Cn = self.D, self.NT, chains
+        cache = [0.0] * NT
+        prog_eval.run(self.prog, self.consts, self.init, self.prog.logpost_prog, self.O, cache=cache)     # terms and statistics at init (amwg_init_kernel)
+        work = np.zeros((2 * NT + 2 * D, Cn))
+        work[:NT, :] = np.asarray(cache)[:, None]
+        state = np.repeat(self.init[:, None], Cn, axis=1).copy()
+        psd = np.full((D, Cn), self.K.hs_exp_of(0.0))
+        acc = np.zeros((D, Cn), dtype=np.int32)
+        vseq = np.zeros((D, Cn), dtype=np.uint16)
+        perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
+        rng_n = np.zeros(Cn, dtype=np.uint64)
+        mon = np.arange(D, dtype=np.int32)
+        out = np.full((sweeps, D, Cn), np.nan)
+        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
+        colp = (C.POINTER(C.c_double) * max(len(cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
+        adapting = np.ones(D, dtype=np.uint8)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        self.K.hs_sweep(p(state, C.c_double), p(psd, C.c_double), p(acc, C.c_int), p(work, C.c_double), p(vseq, C.c_ushort), p(perm, C.c_uint64),
+                        p(rng_n, C.c_uint64), C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), int(D), p(mon, C.c_int),
+                        p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte))
+        return out, rng_n
+
+
+def _agreement(out, ref, params):
+    """fraction of chains whose every recorded row equals the oracle's, and the first row at which any chain differs"""
+    same = None
+    e = 0
+    for pname, pdef in params.items():
+        n = int(np.prod(pdef.get("dim", [1])))
+        got = np.moveaxis(out[:, e:e + n, :], 1, 2)                # [rows, chains, n]
+        want = np.asarray(ref[pname], np.float64).reshape(got.shape)
+        eq = (got.view(np.uint64) == want.view(np.uint64)).all(axis=2)
+        same = eq if same is None else (same & eq)
+        e += n
+    return same.all(axis=0).mean(), same
+
+
+def test_the_statistics_sweep_on_the_host_headline_model(pkg, orc, tmp_path):
+    """BASELINE config 2's model and kernel (resident column, working set in shared memory, two component classes): the production
+    lowering decides steps on differences of factorised plates, so it equals the reference up to rounding -- a decision can differ
+    only when exp(delta) falls within ~1e-13 of the accept uniform. 64 chains x 45 sweeps on the oracle's streams: (nearly) all equal."""
+    x = np.random.default_rng(77).normal(184.5, 4.5, 200)
+    hk = HostStatKernel(pkg, orc, tmp_path, models.PARAMS_NORM, models.norm_post_readme(pkg.ld), x.tolist())
+    assert "#define JWS_SMEM 1" in hk.src and "#define JSTREAM 0" in hk.src
+    out, rng_n = hk.run(64, 5000, 3, 45)
+    ref = orc.run_model("norm_readme", x, models.PARAMS_NORM, chains=64, first_chain=5000, seed=3, burn=0, sample=45)
+    frac, _ = _agreement(out, ref, models.PARAMS_NORM)
+    assert frac >= 0.97, frac
+    assert np.isfinite(out).all() and np.unique(out[-1, 0]).size > 50
+
+
+@pytest.mark.parametrize("J,per,stream", [(8, 32, False), (6, 1500, True), (8, 1100, True)])
+def test_the_statistics_sweep_on_the_host_hierarchical_model(pkg, orc, tmp_path, J, per, stream):
+    """BASELINE config 4's shape: a vector of group means (one class, indices from tables, stepped as an index-ordered block between
+    the steps the chain visits before and after it) and a shared sd whose plate terms are a loop; with 9000 points the column streams
+    through the tile ring (memcpy here)."""
+    rng = np.random.default_rng(4)
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(100, 5, J * per) + np.repeat(rng.normal(0, 3, J), per)
+    P = {"mu": {"type": "real", "dim": [J], "init": 100.0}, "sigma": {"type": "real", "lower": 0, "init": 5.0}}
+    data = {"y": y, "g": g.astype(float)}
+    hk = HostStatKernel(pkg, orc, tmp_path, P, models.hier_norm_post(pkg.ld), data)
+    assert ("#define JSTREAM 1" in hk.src) == stream
+    assert ("#define JBLOCK 0" in hk.src) == (J >= 8)             # the block of group means is stepped in index order from 8 members on
+    chains, sweeps = (32, 45) if not stream else (8, 20)
+    out, rng_n = hk.run(chains, 77, 9, sweeps)
+    ref = orc.run_model("hier_norm", {"y": y, "g": g.astype(float)}, P, chains=chains, first_chain=77, seed=9, burn=0, sample=sweeps)
+    frac, _ = _agreement(out, ref, P)
+    assert frac >= 0.97, frac                                     # measured: 1.0 on all three shapes
+    assert np.isfinite(out).all()
