@@ -286,27 +286,38 @@ class HostKernel(HostProgram):
         self.init = np.array([m.init[c] for c in range(self.D)], dtype=np.float64)
         self.n_params = int(m.n_params)
 
-    def run(self, chains, first_chain, seed, sweeps):
-        """`sweeps` sweeps of sample(): -> out[row][entry][chain] (row r = the state before sweep r), the final state and stream positions"""
+    def start(self, chains, first_chain, seed):
+        """what amwg_create leaves on the device: every chain at `init`, log_post evaluated once, identity substepper order, stream at 0"""
         D, Cn = self.D, chains
-        state = np.repeat(self.init[:, None], Cn, axis=1).copy()
-        psd = np.full((D, Cn), self.K.hs_exp_of(0.0))
-        acc = np.zeros((D, Cn), dtype=np.int32)
+        self.chains, self.first_chain, self.seed = chains, first_chain, seed
+        self.state = np.repeat(self.init[:, None], Cn, axis=1).copy()
+        self.psd = np.full((D, Cn), self.K.hs_exp_of(0.0))
+        self.acc = np.zeros((D, Cn), dtype=np.int32)
         lp0 = self.lib.hs_logpost(self.init.ctypes.data_as(C.POINTER(C.c_double)), -1, 0.0)
-        curr = np.full(Cn, lp0)
-        perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
-        rng_n = np.zeros(Cn, dtype=np.uint64)
+        self.curr = np.full(Cn, lp0)
+        self.perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
+        self.rng_n = np.zeros(Cn, dtype=np.uint64)
+        self.cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
+        self.colp = (C.POINTER(C.c_double) * max(len(self.cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in self.cols])
+        self.adapting = np.ones(D, dtype=np.uint8)
+
+    def sweeps(self, n, record=True, thin=1):
+        """burn(n) (record=False) or sample(n): -> out[row][entry][chain], row r = the state before sweep r * thin"""
         n_der = len(self.s._derived_names)
-        mon = np.arange(D + n_der, dtype=np.int32)
-        out = np.full((sweeps, mon.size, Cn), np.nan)
-        cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
-        colp = (C.POINTER(C.c_double) * max(len(cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
-        adapting = np.ones(D, dtype=np.uint8)
+        mon = np.arange(self.D + n_der, dtype=np.int32)
+        rows = (n + thin - 1) // thin if record else 0
+        out = np.full((max(rows, 1), mon.size, self.chains), np.nan)
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
-        self.K.hs_sweep(p(state, C.c_double), p(psd, C.c_double), p(acc, C.c_int), p(curr, C.c_double), p(perm, C.c_uint64), p(rng_n, C.c_uint64),
-                        C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), C.c_longlong(0), C.c_longlong(1), 1,
-                        int(mon.size), p(mon, C.c_int), p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte))
-        return out, state, rng_n, acc
+        self.K.hs_sweep(p(self.state, C.c_double), p(self.psd, C.c_double), p(self.acc, C.c_int), p(self.curr, C.c_double), p(self.perm, C.c_uint64),
+                        p(self.rng_n, C.c_uint64), C.c_uint64(self.chains), C.c_uint64(self.first_chain), C.c_uint64(self.seed), C.c_longlong(n),
+                        C.c_longlong(0), C.c_longlong(thin), 1 if record else 0, int(mon.size), p(mon, C.c_int), p(out, C.c_double), self.colp,
+                        len(self.cols), p(self.adapting, C.c_ubyte))
+        return out[:rows]
+
+    def run(self, chains, first_chain, seed, sweeps):
+        self.start(chains, first_chain, seed)
+        out = self.sweeps(sweeps)
+        return out, self.state, self.rng_n, self.acc
 
 
 @pytest.mark.parametrize("name,c_model,data_c", [
@@ -490,3 +501,45 @@ def test_the_statistics_sweep_on_the_host_hierarchical_model(pkg, orc, tmp_path,
     frac, _ = _agreement(out, ref, P)
     assert frac >= 0.97, frac                                     # measured: 1.0 on all three shapes
     assert np.isfinite(out).all()
+
+
+@pytest.mark.parametrize("scenario", ["binary_stepper", "binary_component_stepper"])
+def test_the_specialised_kernel_on_the_host_against_the_reference_js_vectors(pkg, orc, tmp_path, scenario):
+    """tests/golden/reference_js.json holds what the UNMODIFIED mcmc.js drew (oracle/minijs). Its two all-binary scenarios need no
+    adaptation kernel (BinaryStepper does not adapt, mcmc.js:740-767), so the emulated specialised kernel can follow their whole scripts
+    -- burn, sample, thinning -- and must reproduce the reference's draws and final state bit for bit, for both recorded chains."""
+    import copy
+    import golden_util as gu
+    cases = [c for c in gu.load()["samplers"] if c["name"] == scenario]
+    assert len(cases) == 2
+    for case in cases:
+        _c, py_model, params, data, _dc = gu.resolve_case(case, pkg)
+        opts = copy.deepcopy(case["options"]) or {}
+        thin = int(opts.pop("thin", 1))
+        assert not opts
+        sub = tmp_path / f"chain{case['chain']}"
+        sub.mkdir()
+        hk = HostKernel(pkg, orc, sub, copy.deepcopy(params), py_model, data)
+        hk.start(1, case["chain"], case["seed"])
+        results = iter(case["results"])
+        for step in case["script"]:
+            if step[0] == "burn":
+                hk.sweeps(step[1], record=False)
+            elif step[0] == "thin":
+                thin = int(step[1])
+            elif step[0] == "sample":
+                want = gu.unhex(next(results)["draws"])
+                out = hk.sweeps(step[1], thin=thin)
+                e = 0
+                for pname in hk.s.params:
+                    n = int(np.prod(hk.s.params[pname]["dim"]))
+                    got = out[:, e:e + n, 0]
+                    assert gu.same(got.reshape(np.asarray(want[pname], dtype=np.float64).shape), want[pname]), (scenario, pname)
+                    e += n
+            else:
+                raise AssertionError(step)
+        e = 0
+        for pname, want in gu.unhex(case["final_state"]).items():
+            n = int(np.prod(hk.s.params[pname]["dim"]))
+            assert gu.same(hk.state[e:e + n, 0], np.asarray(want, dtype=np.float64).reshape(-1)), pname
+            e += n
