@@ -67,9 +67,10 @@ def _skeleton_helpers():
 
 
 class HostProgram:
-    def __init__(self, pkg, orc, tmp_path, params, log_post, data, **opts):
+    def __init__(self, pkg, orc, tmp_path, params, log_post, data, _opts=None, **opts):
         o = {"chains": 4096, "_model_only": True}
         o.update(opts)
+        o.update(_opts or {})                                        # sampler options that may themselves be called `params`
         self.s = s = pkg.mcmc.AmwgSampler(params, log_post, data, o)
         self.prog, self.O = s._program, orc.lib()
         self.consts = prog_eval.fold_constants(self.prog, self.O)
@@ -260,9 +261,9 @@ def _kernel_text(generated):
 
 
 class HostKernel(HostProgram):
-    def __init__(self, pkg, orc, tmp_path, params, log_post, data, **opts):
+    def __init__(self, pkg, orc, tmp_path, params, log_post, data, _opts=None, **opts):
         self._tmp = tmp_path
-        super().__init__(pkg, orc, tmp_path, params, log_post, data, **opts)
+        super().__init__(pkg, orc, tmp_path, params, log_post, data, _opts=_opts, **opts)
         s = self.s
         m = s._model_keepalive[-1]
         rc, msg, src = s.jit_compile_check()
@@ -318,6 +319,61 @@ class HostKernel(HostProgram):
         self.start(chains, first_chain, seed)
         out = self.sweeps(sweeps)
         return out, self.state, self.rng_n, self.acc
+
+    # -- the host side of a sweep call, restated: csrc/amwg_kernels.cu run_sweeps() + amwg_adapt_kernel (mcmc.js:536-551). A launch
+    #    never crosses a batch boundary; at a boundary the component's prop_log_scale moves by +-delta and its counter is cleared.
+    def start_driver(self, first_chain, seed):
+        m = self.s._model_keepalive[-1]
+        self.opts = [m.comp_options[c] for c in range(self.D)]
+        self.start(1, first_chain, seed)
+        self.pls = np.array([[o.prop_log_scale] for o in self.opts], dtype=np.float64)
+        self.psd[:, 0] = [self.K.hs_exp_of(float(v)) for v in self.pls[:, 0]]
+        self.is_adapting = [bool(o.is_adapting) for o in self.opts]
+        self.adapting[:] = [1 if f else 0 for f in self.is_adapting]
+        self.iter_since = [0.0] * self.D
+        self.batch_count = [0.0] * self.D
+
+    def set_adapting(self, flag):
+        self.is_adapting = [bool(flag)] * self.D
+        self.adapting[:] = 1 if flag else 0
+
+    def advance(self, n, record, thin=1):
+        import math
+        n_der = len(self.s._derived_names)
+        mon = np.arange(self.D + n_der, dtype=np.int32)
+        rows = (n + thin - 1) // thin if (record and n > 0) else 0
+        out = np.full((max(rows, 1), mon.size, 1), np.nan)
+        p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+        i0 = 0
+        while i0 < n:
+            L = n - i0
+            for c in range(self.D):
+                if not self.is_adapting[c]:
+                    continue
+                need = math.ceil(self.opts[c].batch_size - self.iter_since[c])
+                if not need >= 1.0:
+                    need = 1.0
+                L = min(L, int(need))
+            self.K.hs_sweep(p(self.state, C.c_double), p(self.psd, C.c_double), p(self.acc, C.c_int), p(self.curr, C.c_double), p(self.perm, C.c_uint64),
+                            p(self.rng_n, C.c_uint64), C.c_uint64(1), C.c_uint64(self.first_chain), C.c_uint64(self.seed), C.c_longlong(L),
+                            C.c_longlong(i0), C.c_longlong(thin), 1 if record else 0, int(mon.size), p(mon, C.c_int), p(out, C.c_double), self.colp,
+                            len(self.cols), p(self.adapting, C.c_ubyte))
+            for c in range(self.D):
+                if not self.is_adapting[c]:
+                    continue
+                self.iter_since[c] += float(L)
+                if self.iter_since[c] >= self.opts[c].batch_size:
+                    self.batch_count[c] += 1.0
+                    adj = self.opts[c].initial_adaptation / math.sqrt(self.batch_count[c])
+                    mx = self.opts[c].max_adaptation
+                    delta = math.nan if (adj != adj or mx != mx) else min(mx, adj)
+                    rate = float(self.acc[c, 0]) / self.opts[c].batch_size if self.opts[c].batch_size != 0 else (math.nan if self.acc[c, 0] == 0 else math.inf)
+                    self.pls[c, 0] = self.pls[c, 0] + delta if rate > self.opts[c].target_accept_rate else self.pls[c, 0] - delta
+                    self.psd[c, 0] = self.K.hs_exp_of(float(self.pls[c, 0]))
+                    self.acc[c, 0] = 0
+                    self.iter_since[c] = 0.0
+            i0 += L
+        return out[:rows]
 
 
 @pytest.mark.parametrize("name,c_model,data_c", [
@@ -543,3 +599,67 @@ def test_the_specialised_kernel_on_the_host_against_the_reference_js_vectors(pkg
             n = int(np.prod(hk.s.params[pname]["dim"]))
             assert gu.same(hk.state[e:e + n, 0], np.asarray(want, dtype=np.float64).reshape(-1)), pname
             e += n
+
+
+def _golden_cases():
+    import golden_util as gu
+    return [pytest.param(c, id=f"{c['name']}-chain{c['chain']}") for c in gu.load()["samplers"]]
+
+
+@pytest.mark.parametrize("case", _golden_cases())
+def test_the_specialised_kernel_on_the_host_follows_the_golden_scripts(pkg, orc, tmp_path, case):
+    """Every sampler scenario of tests/golden/reference_js.json (what the unmodified mcmc.js drew) whose model the full-program
+    specialisation takes -- those that step with a term cache stay on the interpreter kernels and are skipped here: the emulated
+    kernel under the restated host driver (launches that end on batch boundaries, the Roberts-Rosenthal update between them,
+    start/stop_adaptation, thinning, monitors) reproduces the reference's draws, final state and stepper info bit for bit."""
+    import copy
+    import golden_util as gu
+    _c, py_model, params, data, _dc = gu.resolve_case(case, pkg)
+    opts = copy.deepcopy(case["options"]) or {}
+    opts["faithful"] = True
+    try:
+        hk = HostKernel(pkg, orc, tmp_path, copy.deepcopy(params), py_model, data, _opts=opts)
+    except AssertionError as e:
+        if "term cache" in str(e):
+            pytest.skip("steps with a term cache: interpreter kernels")
+        raise
+    hk.start_driver(case["chain"], case["seed"])
+    thin = int(opts.get("thin", 1))
+    names = list(hk.s.params) + list(hk.s._derived_names)
+    width = {k: int(np.prod(hk.s.params[k]["dim"])) for k in hk.s.params}
+    width.update({k: 1 for k in hk.s._derived_names})
+    monitor = opts.get("monitor", None)
+    results = iter(case["results"])
+    for step in case["script"]:
+        op = step[0]
+        if op == "burn": hk.advance(step[1], record=False)
+        elif op == "thin": thin = int(step[1])
+        elif op == "monitor": monitor = step[1]
+        elif op == "stop_adaptation": hk.set_adapting(False)
+        elif op == "start_adaptation": hk.set_adapting(True)
+        elif op == "sample":
+            want = gu.unhex(next(results)["draws"])
+            out = hk.advance(step[1], record=True, thin=abs(thin))
+            keys = names if monitor is None else [k for k in monitor]
+            assert list(want.keys()) == keys
+            e = 0
+            for k in names:
+                if k in want:
+                    got = out[:, e:e + width[k], 0]
+                    assert gu.same(got.reshape(np.asarray(want[k], dtype=np.float64).shape), want[k]), (case["name"], k)
+                e += width[k]
+    e = 0
+    for k in hk.s.params:
+        want = gu.flat_info(case["final_info"].get(k, {}))
+        if want:
+            sl = slice(e, e + width[k])
+            assert gu.same(hk.pls[sl, 0], [w["prop_log_scale"] for w in want]), k
+            assert gu.same(hk.acc[sl, 0].astype(float), [w["acceptance_count"] for w in want]), k
+            assert gu.same(hk.iter_since[sl], [w["iterations_since_adaption"] for w in want]), k
+            assert gu.same(hk.batch_count[sl], [w["batch_count"] for w in want]), k
+        e += width[k]
+    e = 0
+    st = gu.unhex(case["final_state"])
+    for k in hk.s.params:
+        assert gu.same(hk.state[e:e + width[k], 0], np.asarray(st[k], dtype=np.float64).reshape(-1)), k
+        e += width[k]
