@@ -77,6 +77,8 @@ class HostProgram:
         m = s._model_keepalive[-1]
         for i, v in enumerate(self.consts):                           # what try_jit() reads back from the device after folding
             m.consts[i] = float(v)
+        if o.get("_force_full"):                                      # what AMWG_TERM_CACHE=0 does in amwg_create: every step runs the full program
+            m.n_terms = 0
         rc, msg, src = s.jit_compile_check()
         assert rc == 0, msg
         assert "#define JFULL 1" in src
