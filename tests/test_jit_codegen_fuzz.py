@@ -114,3 +114,85 @@ def test_random_models_generated_code_equals_the_program(pkg, orc, tmp_path, blo
         hp.check(np.random.default_rng(seed), trials=120)
         compiled += 1
     assert compiled >= 4, (compiled, declined)
+
+
+# ---- the production lowering: random Normal-plate models, statistics sweep vs full-program sweep (both emulated) ----------------------
+def _build_stat(pkg, seed):
+    ld, mcmc = pkg.ld, pkg.mcmc
+    M = mcmc.Math
+    rng = np.random.default_rng(1000 + seed)
+    J = int(rng.choice([1, 3, 8, 12]))
+    per = int(rng.integers(40, 100))
+    hyper = bool(rng.integers(0, 2)) and J > 1
+    two = bool(rng.integers(0, 2))
+    derived = bool(rng.integers(0, 2))
+    lin = (float(np.round(rng.uniform(0.5, 2.0), 2)), float(np.round(rng.normal(0, 1), 2)))
+    pri = [int(v) for v in rng.integers(0, 5, 4)]
+    centre = float(rng.normal(10, 3))
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(centre, 2.0, J * per) + (np.repeat(rng.normal(0, 1.5, J), per) if J > 1 else 0.0)
+    data = {"y": y.tolist(), "g": g.astype(float).tolist(), "y2": rng.normal(-3, 1.0, 60).tolist()}
+    params = {"sigma": {"type": "real", "lower": 0, "init": 2.0}}
+    if J > 1: params["mu"] = {"type": "real", "dim": [J], "init": centre}
+    else: params["a"] = {"type": "real", "init": centre}
+    if hyper: params.update({"m0": {"type": "real", "init": centre}, "tau": {"type": "real", "lower": 0, "init": 2.0}})
+    if two: params.update({"b": {"type": "real", "init": -3.0}, "s2": {"type": "real", "lower": 0, "init": 1.0}})
+
+    def prior(kind, x, loc, scale):
+        if kind == 0: return ld.norm(x, loc, scale * 20)
+        if kind == 1: return ld.cauchy(x, loc, scale * 5)
+        if kind == 2: return ld.laplace(x, loc, scale * 10)
+        if kind == 3: return ld.logis(x, loc, scale * 8)
+        return ld.unif(x, loc - 100, loc + 100)
+
+    def log_post(state, d):
+        lp = 0
+        if J > 1:
+            for j in range(J):
+                lp += ld.norm(state.mu[j], state.m0, state.tau) if hyper else prior(pri[0], state.mu[j], centre, 1.0)
+        else:
+            lp += prior(pri[0], state.a, centre, 1.0)
+        if hyper:
+            lp += prior(pri[1], state.m0, centre, 2.0)
+            lp += ld.gamma(state.tau, 2, 0.5)
+        lp += ld.gamma(state.sigma, 2, 0.5) if pri[2] < 2 else ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]] if J > 1 else state.a * lin[0] + lin[1], state.sigma)
+        if two:
+            lp += prior(pri[3], state.b, -3.0, 1.0)
+            lp += ld.lnorm(state.s2, 0, 1)
+            for i in range(len(d.y2)):
+                lp += ld.norm(d.y2[i], state.b, state.s2)
+        if derived:
+            state.prec = 1 / (state.sigma * state.sigma)
+        return lp
+    return params, log_post, data
+
+
+@pytest.mark.parametrize("block", range(3))
+def test_random_normal_plate_models_statistics_sweep_equals_full_program_sweep(pkg, orc, tmp_path, block):
+    """The two specialised kernels on the same random model and Philox streams: the statistics sweep (production lowering: one data pass
+    per sweep, steps decided on term differences, component classes / term loops / index-ordered blocks) against the full-program sweep
+    of the bit-faithful lowering. They may differ where exp(delta) falls within rounding of an accept uniform -- in 16 chains x 40 sweeps
+    per model that did not happen once when this was written; the test allows one chain in sixteen."""
+    from test_jit_codegen_semantics import HostKernel, HostStatKernel
+    ran = 0
+    for seed in range(10 * block, 10 * block + 5):
+        params, log_post, data = _build_stat(pkg, seed)
+        sub = tmp_path / f"s{seed}"
+        sub.mkdir()
+        probe = pkg.mcmc.AmwgSampler(params, log_post, data, {"chains": 4096, "_model_only": True})
+        if probe._program.stat_prog < 0:
+            continue                                              # the tracer did not choose the statistics lowering for this one
+        hs = HostStatKernel(pkg, orc, sub, params, log_post, data)
+        (sub / "full").mkdir()
+        hf = HostKernel(pkg, orc, sub / "full", params, log_post, data, faithful=True, _force_full=True)
+        chains, sweeps = 16, 40
+        out_s, _ = hs.run(chains, 31 + seed, 5 + seed, sweeps)
+        out_f, _st, _n, _a = hf.run(chains, 31 + seed, 5 + seed, sweeps)
+        D = hs.D
+        same = (out_s[:, :D, :].view(np.uint64) == out_f[:, :D, :].view(np.uint64)).all(axis=(0, 1))
+        assert same.mean() >= 15 / 16, (seed, same.mean())
+        assert np.isfinite(out_s).all() and np.unique(out_s[-1, 0]).size > 8
+        ran += 1
+    assert ran >= 3, ran
