@@ -576,7 +576,7 @@ static std::string build_source(const amwg_model* md, const std::vector<double>&
   int max_dim0 = 1;
   for (int p = 0; p < P; ++p) {
     if (md->params[p].type == AMWG_BINARY) return "binary parameter";
-    if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, md->params[p].dim0);
+    if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, std::max(md->params[p].dim0, 2));   // >= 2: a [1, n] matrix is multi-component too
   }
   std::string err;
 
@@ -823,7 +823,8 @@ static std::string build_source_full(const amwg_model* md, const std::vector<dou
   const int D = md->n_comp, P = md->n_params;
   if (D > 65535 || P > 255) return "too many components / parameters";
   int max_dim0 = 1;
-  for (int p = 0; p < P; ++p) if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, md->params[p].dim0);
+  // JMAX_DIM0 > 1 is what compiles the multi-component stepping in: a [1, n] matrix (dim0 = 1, tests/test_data.js:176) needs it too
+  for (int p = 0; p < P; ++p) if (md->params[p].n_comp > 1) max_dim0 = std::max(max_dim0, std::max(md->params[p].dim0, 2));
   std::string err;
   Plan& pl = src.plan;
   pl = Plan();

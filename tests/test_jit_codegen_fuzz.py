@@ -196,3 +196,34 @@ def test_random_normal_plate_models_statistics_sweep_equals_full_program_sweep(p
         assert np.isfinite(out_s).all() and np.unique(out_s[-1, 0]).size > 8
         ran += 1
     assert ran >= 3, ran
+
+
+def test_a_one_row_matrix_of_group_means_is_stepped_component_by_component(pkg, orc, tmp_path):
+    """dim [1, n] (tests/test_data.js:176 declares p that way): one top-level entry, n components. The specialised skeletons compile their
+    multi-component stepping in on JMAX_DIM0 > 1 -- which has to hold for such a parameter too (it did not: every round stepped
+    component 0; found by running the hierarchical-binomial golden script through the emulated kernel). Both kernels, same draws."""
+    from test_jit_codegen_semantics import HostKernel, HostStatKernel
+    ld = pkg.ld
+    J, per = 6, 50
+    rng = np.random.default_rng(3)
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(10, 2, J * per) + np.repeat(rng.normal(0, 1.5, J), per)
+    P = {"mu": {"type": "real", "dim": [1, J], "init": 10.0}, "sigma": {"type": "real", "lower": 0, "init": 2.0}}
+
+    def log_post(state, d):
+        lp = 0
+        for j in range(J):
+            lp += ld.norm(state.mu[0][j], 10, 20)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[0][d.g[i]], state.sigma)
+        return lp
+    data = {"y": y.tolist(), "g": g.astype(float).tolist()}
+    hs = HostStatKernel(pkg, orc, tmp_path, P, log_post, data)
+    assert "#define JMAX_DIM0 2" in hs.src
+    (tmp_path / "full").mkdir()
+    hf = HostKernel(pkg, orc, tmp_path / "full", P, log_post, data, faithful=True, _force_full=True)
+    out_s, _ = hs.run(16, 9, 4, 40)
+    out_f, _st, _n, _a = hf.run(16, 9, 4, 40)
+    assert (out_s[:, :J + 1, :].view(np.uint64) == out_f[:, :J + 1, :].view(np.uint64)).all(axis=(0, 1)).mean() >= 15 / 16
+    assert all(np.unique(out_s[-1, c]).size > 8 for c in range(J + 1))          # every component moved
