@@ -227,3 +227,95 @@ def test_a_one_row_matrix_of_group_means_is_stepped_component_by_component(pkg, 
     out_f, _st, _n, _a = hf.run(16, 9, 4, 40)
     assert (out_s[:, :J + 1, :].view(np.uint64) == out_f[:, :J + 1, :].view(np.uint64)).all(axis=(0, 1)).mean() >= 15 / 16
     assert all(np.unique(out_s[-1, c]).size > 8 for c in range(J + 1))          # every component moved
+
+
+# ---- stepping logic over random parameter shapes: the emulated full-program kernel against the oracle's restatement of mcmc.js --------
+def _build_shapes(pkg, seed):
+    ld, mcmc = pkg.ld, pkg.mcmc
+    rng = np.random.default_rng(5000 + seed)
+    n_named = int(rng.choice([1, 2, 3, 5, 18, 21]))
+    params, comps = {}, []                                          # comps: (name, index tuple, type)
+    for k in range(n_named):
+        t = str(rng.choice(["real", "real", "int", "binary"]))
+        shape = rng.choice(["scalar", "vec", "mat", "row"], p=[0.55, 0.2, 0.15, 0.1]) if n_named < 10 else "scalar"
+        dim = {"scalar": None, "vec": [int(rng.integers(2, 6))], "mat": [int(rng.integers(2, 4)), int(rng.integers(2, 4))], "row": [1, int(rng.integers(2, 6))]}[str(shape)]
+        d = {"type": t}
+        if dim: d["dim"] = dim
+        if t == "real" and rng.random() < 0.4: d.update({"lower": -2.0, "upper": 6.0})
+        if t == "int": d.update({"lower": int(rng.integers(-6, 0)), "upper": int(rng.integers(3, 9))})
+        name = "q%d" % k
+        params[name] = d
+        for ix in (np.ndindex(*dim) if dim else [()]):
+            comps.append((name, tuple(int(v) for v in ix), t))
+    locs = rng.normal(1, 1.5, len(comps)).round(2).tolist()
+    couple = [(int(a), int(b)) for a, b in rng.integers(0, len(comps), (min(3, len(comps)), 2))]
+
+    def ref(state, name, ix):
+        v = state[name]
+        for i in ix:
+            v = v[i]
+        return v
+
+    def log_post(state, d=None):
+        lp = 0
+        vals = [ref(state, n, ix) for n, ix, _t in comps]
+        for (n, ix, t), v, loc in zip(comps, vals, locs):
+            lp += ld.bern(v, 0.3 + 0.05 * (len(ix) + 1)) if t == "binary" else ld.norm(v, loc, 1.5)
+        for a, b in couple:                                           # a few couplings: the log_post is not a product of independent factors
+            lp += ld.norm(vals[a] - vals[b], 0.0, 2.0)
+        return lp
+    return params, log_post
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_parameter_shapes_stepping_equals_the_oracle(pkg, orc, tmp_path, seed):
+    """Scalars, vectors, matrices, one-row matrices, real / bounded real / int / binary, up to 21 named parameters (more than 16: the
+    substepper order lives in a per-chain byte array): the emulated specialised kernel's shuffles, visiting orders, proposals, bounds
+    checks and accept decisions against the oracle (mcmc.js restated in C) stepping the same log_post -- the model's bytecode evaluated
+    with the oracle's arithmetic -- on the same Philox streams. Bit for bit, 30 sweeps inside the first adaptation batch."""
+    import prog_eval
+    from test_jit_codegen_semantics import HostKernel
+    params, log_post = _build_shapes(pkg, seed)
+    hk = HostKernel(pkg, orc, tmp_path, params, log_post, None, _force_full=True)
+    sweeps, first, sd = 30, 123 + seed, 77 + seed
+    hk.start(2, first, sd)
+    out = hk.sweeps(sweeps)
+    prog, consts, O = hk.prog, hk.consts, hk.O
+    for c in range(2):
+        o = orc.OracleSampler(lambda st: prog_eval.logpost(prog, consts, st, O), None, params, seed=sd, chain=first + c)
+        refd = o.sample(sweeps)
+        e = 0
+        for name in hk.s.params:
+            n = int(np.prod(hk.s.params[name]["dim"]))
+            want = np.asarray(refd[name], np.float64).reshape(sweeps, n)
+            assert np.array_equal(out[:, e:e + n, c].view(np.uint64), want.view(np.uint64)), (seed, name)
+            e += n
+        assert int(hk.rng_n[c]) == o.rng_position()
+
+
+def test_a_vector_longer_than_256_keeps_its_visiting_order_in_global_memory(pkg, orc, tmp_path):
+    """dim[0] = 260 > 256: the per-sweep visiting order of the parameter is 16-bit rows of a per-chain global array (amwg_tma.cuh
+    ord_get / ord_set) instead of a local byte array. Emulated specialised kernel against the oracle, as above."""
+    import prog_eval
+    from test_jit_codegen_semantics import HostKernel
+    ld = pkg.ld
+    J = 260
+    params = {"x": {"type": "real", "dim": [J]}, "s": {"type": "real", "lower": 0}}
+
+    def lp_wide(state, d=None):
+        lp = ld.gamma(state.s, 2, 1)
+        for j in range(J):
+            lp += ld.norm(state.x[j], 0.01 * j, state.s)
+        return lp
+    hk = HostKernel(pkg, orc, tmp_path, params, lp_wide, None, _force_full=True)
+    assert "#define JMAX_DIM0 260" in hk.s.jit_compile_check()[2]
+    sweeps = 6
+    hk.start(1, 3, 43)
+    assert hk.order_ext is not None
+    out = hk.sweeps(sweeps)
+    prog, consts, O = hk.prog, hk.consts, hk.O
+    o = orc.OracleSampler(lambda st: prog_eval.logpost(prog, consts, st, O), None, params, seed=43, chain=3)
+    ref = o.sample(sweeps)
+    assert np.array_equal(out[:, :J, 0].view(np.uint64), np.asarray(ref["x"], np.float64).reshape(sweeps, J).view(np.uint64))
+    assert np.array_equal(out[:, J, 0].view(np.uint64), np.asarray(ref["s"], np.float64).reshape(sweeps).view(np.uint64))
+    assert int(hk.rng_n[0]) == o.rng_position()

@@ -219,9 +219,10 @@ double hs_exp_of(double x) { return amwg::js_exp(x); }
 void hs_sweep(double* state, double* psd, int* acc, double* curr_lp, unsigned long long* perm, unsigned long long* rng_n,
               unsigned long long C, unsigned long long first_chain, unsigned long long seed, long long n_sweeps, long long sample_i0,
               long long thin, int record, int n_monitor, const int* monitor, double* out, const double** cols, int n_cols,
-              const unsigned char* adapting) {
+              const unsigned char* adapting, unsigned char* perm_ext, unsigned short* order_ext) {
   amwg::JitArgs A{};
   A.a.state = state; A.a.psd = psd; A.a.acc = acc; A.a.curr_lp = curr_lp; A.a.perm = perm; A.a.rng_n = rng_n;
+  A.a.perm_ext = perm_ext; A.a.order_ext = order_ext;           // > 16 named parameters / dim[0] > 256 (amwg_tma.cuh), else null
   A.a.C = C; A.a.first_chain = first_chain; A.a.seed = seed;
   A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = sample_i0; A.sa.thin = thin; A.sa.record = record; A.sa.n_monitor = n_monitor;
   A.sa.monitor = monitor; A.sa.out = out;
@@ -298,11 +299,20 @@ class HostKernel(HostProgram):
         self.acc = np.zeros((D, Cn), dtype=np.int32)
         lp0 = self.lib.hs_logpost(self.init.ctypes.data_as(C.POINTER(C.c_double)), -1, 0.0)
         self.curr = np.full(Cn, lp0)
-        self.perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
+        self.perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)) if self.n_params <= 16 else 0, dtype=np.uint64)
         self.rng_n = np.zeros(Cn, dtype=np.uint64)
         self.cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
         self.colp = (C.POINTER(C.c_double) * max(len(self.cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in self.cols])
         self.adapting = np.ones(D, dtype=np.uint8)
+        m = self.s._model_keepalive[-1]
+        max_dim0 = max([m.params[p].dim0 for p in range(self.n_params) if m.params[p].n_comp > 1] + [1])
+        self.perm_ext = np.repeat(np.arange(self.n_params, dtype=np.uint8)[:, None], Cn, axis=1).copy() if self.n_params > 16 else None
+        self.order_ext = np.zeros((max_dim0, Cn), dtype=np.uint16) if max_dim0 > 256 else None
+
+    def _ext(self):
+        pe = self.perm_ext.ctypes.data_as(C.POINTER(C.c_ubyte)) if self.perm_ext is not None else None
+        oe = self.order_ext.ctypes.data_as(C.POINTER(C.c_ushort)) if self.order_ext is not None else None
+        return pe, oe
 
     def sweeps(self, n, record=True, thin=1):
         """burn(n) (record=False) or sample(n): -> out[row][entry][chain], row r = the state before sweep r * thin"""
@@ -314,7 +324,7 @@ class HostKernel(HostProgram):
         self.K.hs_sweep(p(self.state, C.c_double), p(self.psd, C.c_double), p(self.acc, C.c_int), p(self.curr, C.c_double), p(self.perm, C.c_uint64),
                         p(self.rng_n, C.c_uint64), C.c_uint64(self.chains), C.c_uint64(self.first_chain), C.c_uint64(self.seed), C.c_longlong(n),
                         C.c_longlong(0), C.c_longlong(thin), 1 if record else 0, int(mon.size), p(mon, C.c_int), p(out, C.c_double), self.colp,
-                        len(self.cols), p(self.adapting, C.c_ubyte))
+                        len(self.cols), p(self.adapting, C.c_ubyte), *self._ext())
         return out[:rows]
 
     def run(self, chains, first_chain, seed, sweeps):
@@ -359,7 +369,7 @@ class HostKernel(HostProgram):
             self.K.hs_sweep(p(self.state, C.c_double), p(self.psd, C.c_double), p(self.acc, C.c_int), p(self.curr, C.c_double), p(self.perm, C.c_uint64),
                             p(self.rng_n, C.c_uint64), C.c_uint64(1), C.c_uint64(self.first_chain), C.c_uint64(self.seed), C.c_longlong(L),
                             C.c_longlong(i0), C.c_longlong(thin), 1 if record else 0, int(mon.size), p(mon, C.c_int), p(out, C.c_double), self.colp,
-                            len(self.cols), p(self.adapting, C.c_ubyte))
+                            len(self.cols), p(self.adapting, C.c_ubyte), *self._ext())
             for c in range(self.D):
                 if not self.is_adapting[c]:
                     continue
