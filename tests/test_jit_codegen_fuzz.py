@@ -319,3 +319,67 @@ def test_a_vector_longer_than_256_keeps_its_visiting_order_in_global_memory(pkg,
     assert np.array_equal(out[:, :J, 0].view(np.uint64), np.asarray(ref["x"], np.float64).reshape(sweeps, J).view(np.uint64))
     assert np.array_equal(out[:, J, 0].view(np.uint64), np.asarray(ref["s"], np.float64).reshape(sweeps).view(np.uint64))
     assert int(hk.rng_n[0]) == o.rng_position()
+
+
+def _build_stat_shapes(pkg, seed):
+    """Normal plates whose means are a scalar, a vector, a one-row matrix or a matrix indexed by two data columns, beside parameters
+    that only have priors: bounded reals and ints (their proposals can fall out of bounds: no accept uniform is drawn then)."""
+    ld = pkg.ld
+    rng = np.random.default_rng(9000 + seed)
+    kind = str(rng.choice(["scalar", "vec", "row", "mat"]))
+    n_extra = int(rng.choice([0, 2, 4, 16]))
+    n = int(rng.integers(60, 140))
+    R, Cc = 3, 4
+    g = rng.integers(0, {"scalar": 1, "vec": 5, "row": 5, "mat": R}[kind], n)
+    h = rng.integers(0, Cc, n) if kind == "mat" else np.zeros(n, dtype=np.int64)
+    order = np.lexsort((h, g))                                      # points grouped by the component their mean reads (contiguous plates)
+    g, h = g[order], h[order]
+    y = rng.normal(5, 2, n) + 0.7 * g
+    data = {"y": y.tolist(), "g": g.astype(float).tolist(), "h": h.astype(float).tolist()}
+    params = {"sigma": {"type": "real", "lower": 0, "init": 2.0}}
+    params["mu"] = {"scalar": {"type": "real", "init": 5.0}, "vec": {"type": "real", "dim": [5], "init": 5.0},
+                    "row": {"type": "real", "dim": [1, 5], "init": 5.0}, "mat": {"type": "real", "dim": [R, Cc], "init": 5.0}}[kind]
+    extras = []
+    for k in range(n_extra):
+        t = "int" if k % 3 == 0 else "real"
+        d = {"type": t, "lower": -3 if t == "int" else -1.5, "upper": 4 if t == "int" else 2.5, "init": 0}
+        params["e%d" % k] = d
+        extras.append(("e%d" % k, float(rng.normal(0.5, 1))))
+
+    def log_post(state, d):
+        lp = ld.gamma(state.sigma, 2, 0.5)
+        mu = state.mu
+        if kind == "scalar": lp += ld.norm(mu, 5, 10)
+        elif kind == "vec":
+            for j in range(5): lp += ld.norm(mu[j], 5, 10)
+        elif kind == "row":
+            for j in range(5): lp += ld.cauchy(mu[0][j], 5, 4)
+        else:
+            for r in range(R):
+                for c in range(Cc): lp += ld.norm(mu[r][c], 5, 10)
+        for name, loc in extras:
+            lp += ld.norm(state[name], loc, 1.2)
+        for i in range(len(d.y)):
+            m = mu if kind == "scalar" else (mu[d.g[i]] if kind == "vec" else (mu[0][d.g[i]] if kind == "row" else mu[d.g[i]][d.h[i]]))
+            lp += ld.norm(d.y[i], m, state.sigma)
+        return lp
+    return params, log_post, data
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_shapes_statistics_sweep_equals_full_program_sweep(pkg, orc, tmp_path, seed):
+    from test_jit_codegen_semantics import HostKernel, HostStatKernel
+    params, log_post, data = _build_stat_shapes(pkg, seed)
+    probe = pkg.mcmc.AmwgSampler(params, log_post, data, {"chains": 4096, "_model_only": True})
+    if probe._program.stat_prog < 0:
+        pytest.skip("the tracer did not choose the statistics lowering for this model")
+    hs = HostStatKernel(pkg, orc, tmp_path, params, log_post, data)
+    (tmp_path / "full").mkdir()
+    hf = HostKernel(pkg, orc, tmp_path / "full", params, log_post, data, faithful=True, _force_full=True)
+    chains, sweeps = 12, 35
+    out_s, rng_s = hs.run(chains, 400 + seed, 60 + seed, sweeps)
+    out_f, _st, rng_f, _a = hf.run(chains, 400 + seed, 60 + seed, sweeps)
+    D = hs.D
+    same = (out_s[:, :D, :].view(np.uint64) == out_f[:, :D, :].view(np.uint64)).all(axis=(0, 1))
+    assert same.mean() >= 11 / 12, (seed, same.mean())
+    assert np.array_equal(rng_s[same], rng_f[same])               # and the same number of Math.random() calls

@@ -434,9 +434,11 @@ double hs_exp_of(double x) { return amwg::js_exp(x); }
 int hs_nt() { return JNT; }
 void hs_sweep(double* state, double* psd, int* acc, double* work /* [2 JNT + 2 JD][C] */, unsigned short* vseq, unsigned long long* perm,
               unsigned long long* rng_n, unsigned long long C, unsigned long long first_chain, unsigned long long seed, long long n_sweeps,
-              int n_monitor, const int* monitor, double* out, const double** cols, int n_cols, const unsigned char* adapting) {
+              int n_monitor, const int* monitor, double* out, const double** cols, int n_cols, const unsigned char* adapting,
+              unsigned char* perm_ext, unsigned short* order_ext) {
   amwg::JitArgs A{};
   A.a.state = state; A.a.psd = psd; A.a.acc = acc; A.a.perm = perm; A.a.rng_n = rng_n; A.a.vseq = vseq;
+  A.a.perm_ext = perm_ext; A.a.order_ext = order_ext;
   A.a.tval = work; A.a.tcand = work + (unsigned long long)JNT * C; A.a.bprop = work + 2ull * JNT * C; A.a.bcoin = work + (2ull * JNT + JD) * C;
   A.a.C = C; A.a.first_chain = first_chain; A.a.seed = seed;
   A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = 0; A.sa.thin = 1; A.sa.record = 1; A.sa.n_monitor = n_monitor; A.sa.monitor = monitor; A.sa.out = out;
@@ -508,7 +510,8 @@ class HostStatKernel:
         psd = np.full((D, Cn), self.K.hs_exp_of(0.0))
         acc = np.zeros((D, Cn), dtype=np.int32)
         vseq = np.zeros((D, Cn), dtype=np.uint16)
-        perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)), dtype=np.uint64)
+        perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)) if self.n_params <= 16 else 0, dtype=np.uint64)
+        perm_ext = np.repeat(np.arange(self.n_params, dtype=np.uint8)[:, None], Cn, axis=1).copy() if self.n_params > 16 else None
         rng_n = np.zeros(Cn, dtype=np.uint64)
         mon = np.arange(D, dtype=np.int32)
         out = np.full((sweeps, D, Cn), np.nan)
@@ -518,7 +521,8 @@ class HostStatKernel:
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
         self.K.hs_sweep(p(state, C.c_double), p(psd, C.c_double), p(acc, C.c_int), p(work, C.c_double), p(vseq, C.c_ushort), p(perm, C.c_uint64),
                         p(rng_n, C.c_uint64), C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), int(D), p(mon, C.c_int),
-                        p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte))
+                        p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte),
+                        perm_ext.ctypes.data_as(C.POINTER(C.c_ubyte)) if perm_ext is not None else None, None)
         return out, rng_n
 
 
