@@ -383,3 +383,46 @@ def test_random_shapes_statistics_sweep_equals_full_program_sweep(pkg, orc, tmp_
     same = (out_s[:, :D, :].view(np.uint64) == out_f[:, :D, :].view(np.uint64)).all(axis=(0, 1))
     assert same.mean() >= 11 / 12, (seed, same.mean())
     assert np.array_equal(rng_s[same], rng_f[same])               # and the same number of Math.random() calls
+
+
+def test_statistics_sweep_bounded_block_derived_thinning_and_acceptance_counts(pkg, orc, tmp_path):
+    """A block of eight group means with TIGHT bounds (proposals fall outside: no accept uniform, no evaluation, mcmc.js:520-522 -- the
+    index-ordered block path that cannot pre-draw its uniforms), derived quantities recorded with their state, thinning by 3, and
+    adaptation switched off for half of the components (acceptance counts are only kept where it is on): statistics sweep against
+    full-program sweep, both emulated -- draws, derived values, stream positions and acceptance counters."""
+    from test_jit_codegen_semantics import HostKernel, HostStatKernel
+    ld = pkg.ld
+    J, per = 8, 40
+    rng = np.random.default_rng(12)
+    g = np.repeat(np.arange(J), per)
+    y = rng.normal(10, 2, J * per) + np.repeat(rng.normal(0, 1.5, J), per)
+    P = {"mu": {"type": "real", "dim": [J], "init": 10.0, "lower": 8.5, "upper": 11.5}, "sigma": {"type": "real", "lower": 0, "init": 2.0}}
+
+    def log_post(state, d):
+        lp = 0
+        for j in range(J):
+            lp += ld.norm(state.mu[j], 10, 20)
+        lp += ld.unif(state.sigma, 0, 100)
+        for i in range(len(d.y)):
+            lp += ld.norm(d.y[i], state.mu[d.g[i]], state.sigma)
+        state.prec = 1 / (state.sigma * state.sigma)
+        state.spread = state.mu[0] - state.mu[J - 1]
+        return lp
+    data = {"y": y.tolist(), "g": g.astype(float).tolist()}
+    hs = HostStatKernel(pkg, orc, tmp_path, P, log_post, data)
+    assert "#define JBLOCK 0" in hs.src and "#define JBLOCK_FREE 0" in hs.src and "#define JN_DERIVED 2" in hs.src
+    (tmp_path / "full").mkdir()
+    hf = HostKernel(pkg, orc, tmp_path / "full", P, log_post, data, faithful=True, _force_full=True)
+    chains, sweeps, thin = 16, 45, 3
+    adapting = [c % 2 for c in range(J + 1)]
+    out_s, rng_s = hs.run(chains, 21, 8, sweeps, thin=thin, adapting=adapting)
+    hf.start(chains, 21, 8)
+    hf.adapting[:] = adapting
+    out_f = hf.sweeps(sweeps, thin=thin)
+    assert out_s.shape == out_f.shape == (15, J + 3, chains)
+    same = (out_s.view(np.uint64) == out_f.view(np.uint64)).all(axis=(0, 1))
+    assert same.mean() >= 15 / 16, same.mean()
+    assert np.array_equal(rng_s[same], hf.rng_n[same])
+    assert np.array_equal(hs.acc[:, same], hf.acc[:, same]) and hs.acc[1::2].sum() > 0 and hs.acc[0::2].sum() == 0
+    # the bounds bind: some proposals were refused without a uniform, so the chains consumed different numbers of Math.random() calls
+    assert np.unique(rng_s).size > 4 and out_s[:, :J, :].min() >= 8.5 and out_s[:, :J, :].max() <= 11.5

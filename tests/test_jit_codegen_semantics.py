@@ -435,13 +435,13 @@ int hs_nt() { return JNT; }
 void hs_sweep(double* state, double* psd, int* acc, double* work /* [2 JNT + 2 JD][C] */, unsigned short* vseq, unsigned long long* perm,
               unsigned long long* rng_n, unsigned long long C, unsigned long long first_chain, unsigned long long seed, long long n_sweeps,
               int n_monitor, const int* monitor, double* out, const double** cols, int n_cols, const unsigned char* adapting,
-              unsigned char* perm_ext, unsigned short* order_ext) {
+              unsigned char* perm_ext, unsigned short* order_ext, long long thin) {
   amwg::JitArgs A{};
   A.a.state = state; A.a.psd = psd; A.a.acc = acc; A.a.perm = perm; A.a.rng_n = rng_n; A.a.vseq = vseq;
   A.a.perm_ext = perm_ext; A.a.order_ext = order_ext;
   A.a.tval = work; A.a.tcand = work + (unsigned long long)JNT * C; A.a.bprop = work + 2ull * JNT * C; A.a.bcoin = work + (2ull * JNT + JD) * C;
   A.a.C = C; A.a.first_chain = first_chain; A.a.seed = seed;
-  A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = 0; A.sa.thin = 1; A.sa.record = 1; A.sa.n_monitor = n_monitor; A.sa.monitor = monitor; A.sa.out = out;
+  A.sa.n_sweeps = n_sweeps; A.sa.sample_i0 = 0; A.sa.thin = thin; A.sa.record = 1; A.sa.n_monitor = n_monitor; A.sa.monitor = monitor; A.sa.out = out;
   for (int k = 0; k < n_cols; ++k) A.col[k] = cols[k];
   A.adapting = adapting;
   g_smem_base = amwg::smem;
@@ -500,7 +500,8 @@ class HostStatKernel:
         assert self.NT == self.prog.n_terms
         self.init = np.array([m.init[c] for c in range(self.D)], dtype=np.float64)
 
-    def run(self, chains, first_chain, seed, sweeps):
+    def run(self, chains, first_chain, seed, sweeps, thin=1, adapting=None):
+        """-> out[row][entry][chain] over the D components and the derived quantities, the stream positions; self.acc: acceptance counts"""
         D, NT, Cn = self.D, self.NT, chains
         cache = [0.0] * NT
         prog_eval.run(self.prog, self.consts, self.init, self.prog.logpost_prog, self.O, cache=cache)     # terms and statistics at init (amwg_init_kernel)
@@ -513,16 +514,17 @@ class HostStatKernel:
         perm = np.full(Cn, sum(p << (4 * p) for p in range(self.n_params)) if self.n_params <= 16 else 0, dtype=np.uint64)
         perm_ext = np.repeat(np.arange(self.n_params, dtype=np.uint8)[:, None], Cn, axis=1).copy() if self.n_params > 16 else None
         rng_n = np.zeros(Cn, dtype=np.uint64)
-        mon = np.arange(D, dtype=np.int32)
-        out = np.full((sweeps, D, Cn), np.nan)
+        mon = np.arange(D + len(self.s._derived_names), dtype=np.int32)
+        out = np.full(((sweeps + thin - 1) // thin, mon.size, Cn), np.nan)
         cols = [np.ascontiguousarray(np.asarray(c, dtype=np.float64)) for c in self.prog.columns]
         colp = (C.POINTER(C.c_double) * max(len(cols), 1))(*[c.ctypes.data_as(C.POINTER(C.c_double)) for c in cols])
-        adapting = np.ones(D, dtype=np.uint8)
+        adapting = np.ones(D, dtype=np.uint8) if adapting is None else np.asarray(adapting, dtype=np.uint8)
+        self.acc = acc
         p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
         self.K.hs_sweep(p(state, C.c_double), p(psd, C.c_double), p(acc, C.c_int), p(work, C.c_double), p(vseq, C.c_ushort), p(perm, C.c_uint64),
-                        p(rng_n, C.c_uint64), C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), int(D), p(mon, C.c_int),
+                        p(rng_n, C.c_uint64), C.c_uint64(Cn), C.c_uint64(first_chain), C.c_uint64(seed), C.c_longlong(sweeps), int(mon.size), p(mon, C.c_int),
                         p(out, C.c_double), colp, len(cols), p(adapting, C.c_ubyte),
-                        perm_ext.ctypes.data_as(C.POINTER(C.c_ubyte)) if perm_ext is not None else None, None)
+                        perm_ext.ctypes.data_as(C.POINTER(C.c_ubyte)) if perm_ext is not None else None, None, C.c_longlong(thin))
         return out, rng_n
 
 
